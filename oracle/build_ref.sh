@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE. Compiles the reference's own CPU path, from its
+# sources where they lie (never copied into this repo), plus oracle/ref_driver.cpp, into
+# oracle/_ref/libjpegref.so. The reference's IDE build files are not used.
+# Usage: oracle/build_ref.sh [/root/reference]
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"
+ref="${1:-/root/reference}"
+src="$ref/src"
+if [ ! -f "$src/decoder.cpp" ]; then
+    echo "build_ref: reference sources not found under $src (expected on the GPU box: the prebuilt .so travels)" >&2
+    exit 3
+fi
+mkdir -p "$here/_ref"
+# -DUSE_CPU_ONLY selects the CPU IDCT/colour branch (decoder.cpp:11 has the define commented out);
+# -DNDEBUG turns the reference's int3 asserts off (macro.h:24-31). -O2 as in the reference's Release target.
+g++ -std=c++11 -O2 -fPIC -shared -DNDEBUG -DUSE_CPU_ONLY -w \
+    -I"$src" \
+    "$here/ref_driver.cpp" \
+    "$src/bitstream.cpp" "$src/huffman.cpp" "$src/cpuIDCT8x8.cpp" "$src/decoder.cpp" "$src/parser.cpp" \
+    -o "$here/_ref/libjpegref.so"
+echo "built $here/_ref/libjpegref.so"

@@ -1,0 +1,642 @@
+/*
+ * oracle/oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's CPU algorithm for the baseline-JPEG decode hot path
+ * (xinfushe/oclJPEGDecoder, -DUSE_CPU_ONLY build). It is the checker for the CUDA path: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * it. Nothing under ocljpegdecoder_b200/ links, imports or calls it, and the product path has
+ * no CPU fallback.
+ *
+ * Parity status: PINNED. tests/test_oracle.py checks this restatement
+ *   (a) against the golden SHA-256s of the reference's own fixture
+ *       test/JPEG_example_JPG_RIP_050.jpg (coefficient tap c25806f5..., pixel tap efb49cf9...),
+ *   (b) against the unmodified reference compiled from /root/reference/src
+ *       (oracle/_ref/libjpegref.so, see oracle/build_ref.sh) on synthetic 4:4:4 / 4:2:0 / 4:2:2
+ *       streams with and without restart markers, bit for bit on both taps.
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * This is a restatement of behaviour, written from the survey's normative appendix (SURVEY.md
+ * App. A); no reference source text is reproduced.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_OK 0
+#define ORC_E_FORMAT (-1)      /* container malformed / reference would stop parsing        */
+#define ORC_E_UNSUPPORTED (-2) /* rejected by the accept gate (decoder.cpp:18-70)           */
+#define ORC_E_DATA (-3)        /* entropy-coded data corrupt / truncated / RST mismatch     */
+#define ORC_E_NOMEM (-4)
+
+/* flags for orc_parse */
+#define ORC_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: only (22,11,11) and (11,11,11)   */
+#define ORC_GATE_EXTENDED 1  /* also 4:2:2 (21,11,11) and 4:4:0 (12,11,11): the CPU loops of */
+                             /* decoder.cpp:429-495 are generic for 1x1 chroma  */
+
+typedef struct
+{
+    int32_t num_codes;
+    uint8_t length[256];  /* code length of the n-th code in DHT order                      */
+    uint16_t code[256];   /* canonical code value, right-aligned                            */
+    uint8_t value[256];   /* symbol                                                         */
+} orc_huff;
+
+typedef struct
+{
+    int32_t width, height;
+    int32_t sampling[3];   /* (h<<4)|v as in SOF0 (jpeg.h:26)                               */
+    int32_t quant_id[3];
+    int32_t huff_id[3];    /* (dc<<4)|ac as in SOS (jpeg.h:37)                              */
+    int32_t restart_interval;
+    int32_t mcu_width, mcu_height; /* pixels                                               */
+    int32_t mcu_count_w, mcu_count_h, mcu_count;
+    int32_t blks_per_mcu[3];
+    int32_t tot_blks_per_mcu;
+    int32_t blk_count;
+    int64_t scan_offset;   /* file offset of the first entropy-coded byte                   */
+    int32_t quant_present[4];
+    int32_t quant[4][64];  /* file (zig-zag) order, as parser.cpp:65-86 keeps them          */
+    int32_t huff_present[32]; /* index = (Tc<<4)|Th, parser.cpp:176-177                     */
+    orc_huff huff[32];
+} orc_image;
+
+/* ------------------------------------------------------------------------------------------ */
+/* zig-zag: table[i] = natural (row-major) index of the i-th coefficient in scan order.       */
+/* Follows the walk of zigzag.h:15-40 (start going up-right, bounce off the edges).           */
+static int g_zigzag[64];
+static int g_zigzag_ready = 0;
+
+static void orc_init_zigzag(void)
+{
+    int x = 0, y = 0, dx = 1, dy = -1, i;
+    for (i = 0; i < 64; i++)
+    {
+        g_zigzag[i] = y * 8 + x;
+        {
+            const int nx = x + dx, ny = y + dy;
+            if (nx < 0 || nx >= 8 || ny < 0 || ny >= 8)
+            {
+                if (x < 7 && y < 7) { if (dx > 0) x++; else y++; }
+                else                { if (dx < 0) x++; else y++; }
+                dx = -dx; dy = -dy;
+            }
+            else { x = nx; y = ny; }
+        }
+    }
+    g_zigzag_ready = 1;
+}
+
+const int *orc_zigzag(void)
+{
+    if (!g_zigzag_ready) orc_init_zigzag();
+    return g_zigzag;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Container parsing: restates load_jpg()'s marker loop (parser.cpp:272-419) and the segment   */
+/* readers it calls, reading from memory instead of a FILE*.                                   */
+
+typedef struct { const uint8_t *p; size_t len, pos; } orc_rd;
+
+static int rd_bytes(orc_rd *r, void *dst, size_t n)
+{
+    if (r->pos + n > r->len) return 0;
+    if (dst) memcpy(dst, r->p + r->pos, n);
+    r->pos += n;
+    return 1;
+}
+
+/* parser.cpp:47-100 */
+static int orc_read_dqt(orc_image *img, orc_rd *r, size_t len)
+{
+    while (len > 0)
+    {
+        uint8_t byte = 0, raw[128];
+        int prec, id, i;
+        /* the reference ignores fread's result here; a short read leaves `byte` undefined.   */
+        if (!rd_bytes(r, &byte, 1)) return 0;
+        prec = byte >> 4;
+        id = byte & 0xF;
+        if (id > 3 || img->quant_present[id]) return 0;
+        if (prec != 0 && prec != 1) return 0;
+        if (!rd_bytes(r, raw, prec ? 128 : 64)) return 0;
+        for (i = 0; i < 64; i++)
+        {
+            /* 16-bit tables are read as raw host-order uint16 WITHOUT a byte swap             */
+            /* (parser.cpp:81-87); on a little-endian host that is lo | hi<<8.                 */
+            img->quant[id][i] = prec ? (raw[2 * i] | (raw[2 * i + 1] << 8)) : raw[i];
+        }
+        img->quant_present[id] = 1;
+        if (len >= (size_t)64 * (prec + 1) + 1) len -= (size_t)64 * (prec + 1) + 1;
+        else return 0;
+    }
+    return 1;
+}
+
+/* parser.cpp:102-130 */
+static int orc_read_sof(orc_image *img, orc_rd *r, size_t len)
+{
+    uint8_t b[15];
+    int i;
+    if (len != 15 || !rd_bytes(r, b, 15)) return 0;
+    if (b[5] != 3 || b[0] != 8) return 0;
+    img->height = (b[1] << 8) | b[2];
+    img->width = (b[3] << 8) | b[4];
+    for (i = 0; i < 3; i++)
+    {
+        img->sampling[i] = b[6 + 3 * i + 1];
+        img->quant_id[i] = b[6 + 3 * i + 2];
+    }
+    return 1;
+}
+
+/* parser.cpp:132-154 */
+static int orc_read_sos(orc_image *img, orc_rd *r, size_t len)
+{
+    uint8_t b[10];
+    int i;
+    if (len != 10 || !rd_bytes(r, b, 10)) return 0;
+    if (b[7] != 0 || b[8] != 0x3F || b[9] != 0) return 0;
+    if (b[0] != 3) return 0;
+    for (i = 0; i < 3; i++) img->huff_id[i] = b[1 + 2 * i + 1];
+    return 1;
+}
+
+/* parser.cpp:156-168 */
+static int orc_read_dri(orc_image *img, orc_rd *r, size_t len)
+{
+    uint8_t b[2];
+    if (len != 2 || !rd_bytes(r, b, 2)) return 0;
+    img->restart_interval = (b[0] << 8) | b[1];
+    return 1;
+}
+
+/* parser.cpp:170-270. Canonical code assignment: the first code is all zeros at the first      */
+/* populated length; each next code is previous+1, left-shifted when the length grows           */
+/* (parser.cpp:221-257 does this on ASCII strings).                                             */
+static int orc_read_dht(orc_image *img, orc_rd *r, size_t len)
+{
+    while (len > 0)
+    {
+        uint8_t byte = 0, counts[16];
+        int type, id, i, total = 0;
+        orc_huff *t;
+        if (!rd_bytes(r, &byte, 1)) return 0;
+        type = byte >> 4;
+        id = byte & 0x1F;
+        if (type != 0 && type != 1) return 0;
+        if (img->huff_present[id]) return 0;
+        t = &img->huff[id];
+        img->huff_present[id] = 1;
+        t->num_codes = 0;
+        if (!rd_bytes(r, counts, 16)) return 0;
+        for (i = 0; i < 16; i++) total += counts[i];
+        if (total > 256) return 0;
+        t->num_codes = total;
+        if (total > 0)
+        {
+            int n = 0, l;
+            uint32_t code = 0;
+            if (!rd_bytes(r, t->value, (size_t)total)) return 0;
+            for (l = 1; l <= 16; l++)
+            {
+                for (i = 0; i < counts[l - 1]; i++)
+                {
+                    /* incrementing an all-ones string fails in the reference (parser.cpp:239) */
+                    if (code >> l) return 0;
+                    t->length[n] = (uint8_t)l;
+                    t->code[n] = (uint16_t)code;
+                    n++;
+                    code++;
+                }
+                code <<= 1;
+            }
+        }
+        if (len >= (size_t)16 + total + 1) len -= (size_t)16 + total + 1;
+        else return 0;
+    }
+    return 1;
+}
+
+/* decoder.cpp:18-70 */
+static int orc_is_supported(const orc_image *img, int gate)
+{
+    int i;
+    if (img->width <= 0 || img->height <= 0) return 0;
+    for (i = 0; i < 3; i++)
+        if (img->quant_id[i] > 3 || !img->quant_present[img->quant_id[i]]) return 0;
+    for (i = 0; i < 3; i++)
+    {
+        const int ac = img->huff_id[i] & 0xF, dc = img->huff_id[i] >> 4;
+        if (!img->huff_present[dc]) return 0;
+        if (!img->huff_present[ac | 0x10]) return 0;
+    }
+    if (img->sampling[1] != 0x11 || img->sampling[2] != 0x11) return 0;
+    if (img->sampling[0] == 0x22 || img->sampling[0] == 0x11) return 1;
+    if (gate == ORC_GATE_EXTENDED && (img->sampling[0] == 0x21 || img->sampling[0] == 0x12)) return 1;
+    return 0;
+}
+
+/* decoder.cpp:161-199 (geometry only) */
+static void orc_geometry(orc_image *img)
+{
+    int i, mh = 0, mv = 0;
+    img->tot_blks_per_mcu = 0;
+    for (i = 0; i < 3; i++)
+    {
+        const int h = img->sampling[i] >> 4, v = img->sampling[i] & 0xF;
+        if (h > mh) mh = h;
+        if (v > mv) mv = v;
+        img->blks_per_mcu[i] = h * v;
+        img->tot_blks_per_mcu += h * v;
+    }
+    img->mcu_width = mh * 8;
+    img->mcu_height = mv * 8;
+    img->mcu_count_w = (img->width - 1) / img->mcu_width + 1;
+    img->mcu_count_h = (img->height - 1) / img->mcu_height + 1;
+    img->mcu_count = img->mcu_count_w * img->mcu_count_h;
+    img->blk_count = img->tot_blks_per_mcu * img->mcu_count;
+}
+
+/* load_jpg(), parser.cpp:272-419: SOI, then APPn directly after SOI are skipped, then           */
+/* DQT/SOF0/DHT/DRI until SOS; any other marker ends parsing. Only the second byte of each       */
+/* 2-byte tag is examined (parser.cpp:295,327,414).                                              */
+int orc_parse(const uint8_t *file, size_t len, int gate, orc_image *img)
+{
+    orc_rd r;
+    uint8_t tag[2], lb[2];
+    r.p = file; r.len = len; r.pos = 0;
+    memset(img, 0, sizeof(*img));
+    if (!rd_bytes(&r, tag, 2) || tag[0] != 0xFF || tag[1] != 0xD8) return ORC_E_FORMAT;
+    tag[1] = 0;
+    while (rd_bytes(&r, tag, 2) && tag[1] >= 0xE0 && tag[1] <= 0xEF)
+    {
+        size_t l;
+        if (!rd_bytes(&r, lb, 2)) return ORC_E_FORMAT;
+        l = (size_t)((lb[0] << 8) | lb[1]);
+        if (l < 2 || r.pos + (l - 2) > r.len) return ORC_E_FORMAT;
+        r.pos += l - 2;
+        tag[1] = 0;
+    }
+    while (tag[1] != 0)
+    {
+        size_t seglen;
+        if (!rd_bytes(&r, lb, 2)) return ORC_E_FORMAT;
+        seglen = (uint16_t)(((lb[0] << 8) | lb[1]) - 2);
+        switch (tag[1])
+        {
+        case 0xDB: if (!orc_read_dqt(img, &r, seglen)) return ORC_E_FORMAT; break;
+        case 0xC0: if (!orc_read_sof(img, &r, seglen)) return ORC_E_FORMAT; break;
+        case 0xC4: if (!orc_read_dht(img, &r, seglen)) return ORC_E_FORMAT; break;
+        case 0xDD: if (!orc_read_dri(img, &r, seglen)) return ORC_E_FORMAT; break;
+        case 0xDA:
+            if (!orc_read_sos(img, &r, seglen)) return ORC_E_FORMAT;
+            if (!orc_is_supported(img, gate)) return ORC_E_UNSUPPORTED;
+            orc_geometry(img);
+            img->scan_offset = (int64_t)r.pos;
+            return ORC_OK;
+        default: /* SOF1..3 (parser.cpp:347-352), EOI, COM, late APPn, ...: parsing ends */
+            return ORC_E_FORMAT;
+        }
+        if (!rd_bytes(&r, tag, 2)) return ORC_E_FORMAT;
+    }
+    return ORC_E_FORMAT;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Entropy-coded segment -> clean byte stream: read_more_data<>(), decoder.cpp:94-159.         */
+/*   FF 00 -> FF ; FF D0..D7 -> Dn (the FF is dropped, the Dn byte stays in the stream) ;      */
+/*   FF FF -> first FF dropped, second re-examined ; FF D9 -> end ; FF xx (other) -> end.      */
+/* (The reference processes 2 KiB fread chunks and, on "other", also loses the bytes of the    */
+/* current chunk that precede the marker -- a chunk-phase artefact of an already failing       */
+/* stream that is not restated.)                                                               */
+static size_t orc_unstuff(const uint8_t *src, size_t n, uint8_t *dst)
+{
+    size_t i = 0, o = 0;
+    while (i < n)
+    {
+        const uint8_t b = src[i];
+        if (b != 0xFF) { dst[o++] = b; i++; continue; }
+        if (i + 1 >= n) break; /* the reference's sentinel/extra fread finds nothing: stop      */
+        {
+            const uint8_t m = src[i + 1];
+            if (m == 0x00) { dst[o++] = 0xFF; i += 2; }
+            else if (m >= 0xD0 && m <= 0xD7) { dst[o++] = m; i += 2; }
+            else if (m == 0xFF) { i += 1; }
+            else break; /* EOI or any other marker */
+        }
+    }
+    return o;
+}
+
+/* MSB-first bit reader over the clean stream. Equivalent to BitStream's cached ops             */
+/* (bitstream.h:311-365) for every position inside the stream; reads past the end yield zeros   */
+/* and are reported through `overrun` (the reference's cacheEof(), bitstream.h:322-331).        */
+typedef struct { const uint8_t *p; size_t nbytes; uint64_t bitpos; } orc_bits;
+
+static uint32_t bits_peek(const orc_bits *b, int n) /* n <= 32 */
+{
+    uint64_t v = 0;
+    size_t byte = (size_t)(b->bitpos >> 3);
+    int i;
+    if (n == 0) return 0;
+    for (i = 0; i < 5; i++)
+    {
+        v = (v << 8) | (byte + (size_t)i < b->nbytes ? b->p[byte + i] : 0);
+    }
+    v <<= 24 + (b->bitpos & 7);           /* align the first wanted bit to bit 63 */
+    return (uint32_t)(v >> (64 - n));
+}
+
+static void bits_skip(orc_bits *b, int n) { b->bitpos += (uint64_t)n; }
+static int bits_overrun(const orc_bits *b) { return b->bitpos > (uint64_t)b->nbytes * 8; }
+
+/* One Huffman symbol: HuffmanTree<16,uint8_t>::findCodeInCache(), huffman.h:277-314. The       */
+/* reference walks a 16-ary trie over a 16-bit window; for a prefix-free code set that is the   */
+/* unique codeword that prefixes the window, or failure when none does.                          */
+static int orc_decode_symbol(orc_bits *b, const orc_huff *t)
+{
+    const uint32_t win = bits_peek(b, 16);
+    int n;
+    for (n = 0; n < t->num_codes; n++)
+    {
+        const int l = t->length[n];
+        if ((win >> (16 - l)) == t->code[n])
+        {
+            bits_skip(b, l);
+            return t->value[n];
+        }
+    }
+    return -1;
+}
+
+/* convert_number()/read_number(), decoder.cpp:72-92 (JPEG EXTEND; 0 bits -> 0). */
+static int32_t orc_read_number(orc_bits *b, int nbits)
+{
+    int32_t v;
+    if (nbits == 0) return 0;
+    v = (int32_t)bits_peek(b, nbits);
+    bits_skip(b, nbits);
+    if (!(v >> (nbits - 1))) v = v + 1 - (int32_t)(1u << nbits);
+    return v;
+}
+
+/* decode_huffman_block(), decoder.cpp:221-260. coef[] is in scan (zig-zag) order, pre-zeroed. */
+static int orc_decode_block(orc_bits *b, int32_t *last_dc, int32_t coef[64], const orc_huff *dc, const orc_huff *ac)
+{
+    int count = 0, sym;
+    sym = orc_decode_symbol(b, dc);
+    if (sym < 0) return 0;
+    if (sym > 25) return 0; /* the reference only asserts hval<=25 (decoder.cpp:230); >32 bits is undefined there */
+    *last_dc += orc_read_number(b, sym);
+    coef[count++] = *last_dc;
+    while (count < 64)
+    {
+        int run, size;
+        sym = orc_decode_symbol(b, ac);
+        if (sym < 0) return 0;
+        run = sym >> 4;
+        size = sym & 0xF;
+        count += run;
+        if (size == 0)
+        {
+            if (run == 0) break; /* EOB */
+            count++;             /* any other run with size 0 skips run+1 zeros (decoder.cpp:247-252) */
+        }
+        else
+        {
+            const int32_t v = orc_read_number(b, size);
+            if (count < 64) coef[count] = v; /* the reference writes out of bounds here and then fails */
+            count++;
+        }
+    }
+    return count <= 64;
+}
+
+/* decode_huffman_data(), decoder.cpp:262-365. mcu_data = int32[blk_count][64], natural order,   */
+/* dequantised, MCU-interleaved block order, padding MCUs included.                              */
+int orc_huffman(const orc_image *img, const uint8_t *file, size_t len, int32_t *mcu_data)
+{
+    const int *zz = orc_zigzag();
+    uint8_t *clean;
+    orc_bits b;
+    int32_t dc_pred[3] = {0, 0, 0};
+    int mcu, ch, blk, out_blk = 0, dri_mcu_counter = 0, dri_counter = 0, rc = ORC_OK;
+    if (img->scan_offset < 0 || (size_t)img->scan_offset > len) return ORC_E_DATA;
+    clean = (uint8_t *)malloc(len - (size_t)img->scan_offset + 16);
+    if (!clean) return ORC_E_NOMEM;
+    b.p = clean;
+    b.nbytes = orc_unstuff(file + img->scan_offset, len - (size_t)img->scan_offset, clean);
+    b.bitpos = 0;
+    for (mcu = 0; mcu < img->mcu_count && rc == ORC_OK; mcu++)
+    {
+        if (img->restart_interval > 0 && dri_mcu_counter++ == img->restart_interval)
+        {
+            uint32_t rst;
+            b.bitpos = (b.bitpos + 7) & ~(uint64_t)7;      /* cacheAlignToByte(), bitstream.h:362 */
+            rst = bits_peek(&b, 8);
+            bits_skip(&b, 8);
+            if (rst != (uint32_t)(0xD0 + (dri_counter & 7))) { rc = ORC_E_DATA; break; }
+            dri_mcu_counter -= img->restart_interval;
+            dri_counter++;
+            dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
+        }
+        for (ch = 0; ch < 3 && rc == ORC_OK; ch++)
+        {
+            const int32_t *qt = img->quant[img->quant_id[ch]];
+            const orc_huff *dc = &img->huff[img->huff_id[ch] >> 4];
+            const orc_huff *ac = &img->huff[0x10 | (img->huff_id[ch] & 0xF)];
+            if ((mcu > 0 || ch > 0) && bits_overrun(&b)) { rc = ORC_E_DATA; break; }
+            for (blk = 0; blk < img->blks_per_mcu[ch]; blk++)
+            {
+                int32_t mat[64];
+                int32_t *dst = mcu_data + (size_t)out_blk * 64;
+                int pos;
+                memset(mat, 0, sizeof(mat));
+                if (!orc_decode_block(&b, &dc_pred[ch], mat, dc, ac)) { rc = ORC_E_DATA; break; }
+                for (pos = 0; pos < 64; pos++) dst[zz[pos]] = mat[pos] * qt[pos]; /* decoder.cpp:338-341 */
+                out_blk++;
+            }
+        }
+    }
+    free(clean);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Chen-Wang integer IDCT: cpuIDCT8x8.cpp:6-127. Rows first, then columns, in place, int32.     */
+#define W1 2841
+#define W2 2676
+#define W3 2408
+#define W5 1609
+#define W6 1108
+#define W7 565
+
+static int32_t orc_iclp(int32_t v) /* cpuIDCT8x8.cpp:13-23: clip to [-256,255] */
+{
+    return v < -256 ? -256 : (v > 255 ? 255 : v);
+}
+
+/* cpuIDCT8x8.cpp:36-80. The all-AC-zero shortcut (:40-45) equals the general path:             */
+/* ((b0<<11)+128)>>8 == b0<<3, so it is not restated separately.                                */
+static void orc_idct_row(int32_t *blk)
+{
+    int32_t x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    x1 = blk[4] * 2048; x2 = blk[6]; x3 = blk[2]; x4 = blk[1]; x5 = blk[7]; x6 = blk[5]; x7 = blk[3];
+    x0 = blk[0] * 2048 + 128;
+    x8 = W7 * (x4 + x5);
+    x4 = x8 + (W1 - W7) * x4;
+    x5 = x8 - (W1 + W7) * x5;
+    x8 = W3 * (x6 + x7);
+    x6 = x8 - (W3 - W5) * x6;
+    x7 = x8 - (W3 + W5) * x7;
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = W6 * (x3 + x2);
+    x2 = x1 - (W2 + W6) * x2;
+    x3 = x1 + (W2 - W6) * x3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (181 * (x4 + x5) + 128) >> 8;
+    x4 = (181 * (x4 - x5) + 128) >> 8;
+    blk[0] = (x7 + x1) >> 8;
+    blk[1] = (x3 + x2) >> 8;
+    blk[2] = (x0 + x4) >> 8;
+    blk[3] = (x8 + x6) >> 8;
+    blk[4] = (x8 - x6) >> 8;
+    blk[5] = (x0 - x4) >> 8;
+    blk[6] = (x3 - x2) >> 8;
+    blk[7] = (x7 - x1) >> 8;
+}
+
+/* cpuIDCT8x8.cpp:82-127. Shortcut (:86-92): (b0+32)>>6 == ((b0<<8)+8192)>>14.                   */
+static void orc_idct_col(int32_t *blk)
+{
+    int32_t x0, x1, x2, x3, x4, x5, x6, x7, x8;
+    x1 = blk[8 * 4] * 256; x2 = blk[8 * 6]; x3 = blk[8 * 2]; x4 = blk[8 * 1];
+    x5 = blk[8 * 7]; x6 = blk[8 * 5]; x7 = blk[8 * 3];
+    x0 = blk[0] * 256 + 8192;
+    x8 = W7 * (x4 + x5) + 4;
+    x4 = (x8 + (W1 - W7) * x4) >> 3;
+    x5 = (x8 - (W1 + W7) * x5) >> 3;
+    x8 = W3 * (x6 + x7) + 4;
+    x6 = (x8 - (W3 - W5) * x6) >> 3;
+    x7 = (x8 - (W3 + W5) * x7) >> 3;
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = W6 * (x3 + x2) + 4;
+    x2 = (x1 - (W2 + W6) * x2) >> 3;
+    x3 = (x1 + (W2 - W6) * x3) >> 3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (181 * (x4 + x5) + 128) >> 8;
+    x4 = (181 * (x4 - x5) + 128) >> 8;
+    blk[8 * 0] = orc_iclp((x7 + x1) >> 14);
+    blk[8 * 1] = orc_iclp((x3 + x2) >> 14);
+    blk[8 * 2] = orc_iclp((x0 + x4) >> 14);
+    blk[8 * 3] = orc_iclp((x8 + x6) >> 14);
+    blk[8 * 4] = orc_iclp((x8 - x6) >> 14);
+    blk[8 * 5] = orc_iclp((x0 - x4) >> 14);
+    blk[8 * 6] = orc_iclp((x3 - x2) >> 14);
+    blk[8 * 7] = orc_iclp((x7 - x1) >> 14);
+}
+
+/* Fast_IDCT(), cpuIDCT8x8.cpp:25-34 */
+void orc_idct(int32_t *block)
+{
+    int i;
+    for (i = 0; i < 8; i++) orc_idct_row(block + 8 * i);
+    for (i = 0; i < 8; i++) orc_idct_col(block + i);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* clamp255 / RGBClamp32 / YUV_to_RGB32: macro.h:121-145, decoder.cpp:367-370.                  */
+/* IEEE double, left to right, C truncation; bytes in memory are B,G,R,0.                       */
+static uint32_t orc_clamp255(int n) { return n < 0 ? 0u : (n > 255 ? 255u : (uint32_t)n); }
+
+uint32_t orc_yuv_to_rgb32(int32_t Y, int32_t U, int32_t V)
+{
+    const int r = (int)(Y + 1.402 * V + 128);
+    const int g = (int)(Y - 0.34414 * U - 0.71414 * V + 128);
+    const int b = (int)(Y + 1.772 * U + 128);
+    return (orc_clamp255(r) << 16) | (orc_clamp255(g) << 8) | orc_clamp255(b);
+}
+
+/* decode_mcu_data(), CPU branch, decoder.cpp:429-495: IDCT every block in place, then for each  */
+/* pixel of each MCU pick Y by block, chroma by pixel replication (integer division by the       */
+/* sampling ratio), convert, and keep pixels with x<W, y<H (the reference's BMP additionally     */
+/* carries (mcu_count_h*mcu_height - H) junk rows that no consumer reads).           */
+/* mcu_data is transformed in place like the reference does. bgra: H rows of W*4 bytes.          */
+int orc_pixels(const orc_image *img, int32_t *mcu_data, uint8_t *bgra)
+{
+    const int yh = img->sampling[0] >> 4, yv = img->sampling[0] & 0xF, yn = yh * yv;
+    const int ruh = yh / (img->sampling[1] >> 4), ruv = yv / (img->sampling[1] & 0xF);
+    const int rvh = yh / (img->sampling[2] >> 4), rvv = yv / (img->sampling[2] & 0xF);
+    int my, mx, blk, x, y;
+    size_t out_blk = 0;
+    if (img->blks_per_mcu[1] != 1 || img->blks_per_mcu[2] != 1) return ORC_E_UNSUPPORTED;
+    for (my = 0; my < img->mcu_count_h; my++)
+    {
+        for (mx = 0; mx < img->mcu_count_w; mx++)
+        {
+            int32_t *mat = mcu_data + out_blk * 64;
+            for (blk = 0; blk < img->tot_blks_per_mcu; blk++) orc_idct(mat + blk * 64);
+            out_blk += (size_t)img->tot_blks_per_mcu;
+            for (y = 0; y < img->mcu_height; y++)
+            {
+                const int py = my * img->mcu_height + y;
+                if (py >= img->height) break;
+                for (x = 0; x < img->mcu_width; x++)
+                {
+                    const int px = mx * img->mcu_width + x;
+                    int32_t Y, U, V;
+                    uint32_t rgb;
+                    uint8_t *o;
+                    if (px >= img->width) break;
+                    Y = mat[((y >> 3) * yh + (x >> 3)) * 64 + (((y & 7) << 3) | (x & 7))];
+                    U = mat[yn * 64 + ((y / ruv) << 3) + x / ruh];
+                    V = mat[(yn + 1) * 64 + ((y / rvv) << 3) + x / rvh];
+                    rgb = orc_yuv_to_rgb32(Y, U, V);
+                    o = bgra + ((size_t)py * img->width + px) * 4;
+                    o[0] = (uint8_t)rgb; o[1] = (uint8_t)(rgb >> 8); o[2] = (uint8_t)(rgb >> 16); o[3] = (uint8_t)(rgb >> 24);
+                }
+            }
+        }
+    }
+    return ORC_OK;
+}
+
+/* Convenience for the checkers: sizes, and the whole path in one call. */
+size_t orc_sizeof_image(void) { return sizeof(orc_image); }
+
+int orc_decode(const uint8_t *file, size_t len, int gate, orc_image *img, int32_t *coef_out, size_t coef_cap, uint8_t *bgra_out, size_t bgra_cap)
+{
+    int rc = orc_parse(file, len, gate, img);
+    int32_t *work;
+    size_t ncoef;
+    if (rc != ORC_OK) return rc;
+    ncoef = (size_t)img->blk_count * 64;
+    if (!coef_out && !bgra_out) return ORC_OK;
+    if (coef_out && coef_cap < ncoef) return ORC_E_NOMEM;
+    if (bgra_out && bgra_cap < (size_t)img->width * img->height * 4) return ORC_E_NOMEM;
+    work = (int32_t *)malloc(ncoef * sizeof(int32_t));
+    if (!work) return ORC_E_NOMEM;
+    rc = orc_huffman(img, file, len, work);
+    if (rc == ORC_OK && coef_out) memcpy(coef_out, work, ncoef * sizeof(int32_t));
+    if (rc == ORC_OK && bgra_out) rc = orc_pixels(img, work, bgra_out);
+    free(work);
+    return rc;
+}
