@@ -1,0 +1,41 @@
+# Builds the product library (CUDA, sm_100a only) and the test-infrastructure oracle.
+NVCC ?= nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+CSRC := ocljpegdecoder_b200/csrc
+LIBDIR := ocljpegdecoder_b200/lib
+BINDIR := ocljpegdecoder_b200/bin
+OBJDIR := build
+
+LIB := $(LIBDIR)/libb2j.so
+OBJS := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/host_parse.o $(OBJDIR)/huff_lut.o
+HDRS := $(wildcard $(CSRC)/*.h) include/b2j.h
+
+all: $(LIB) mathcheck oracle
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+# host-side unit-check helper: the device arithmetic header + the LUT builder compiled with g++
+mathcheck: tests/native/libb2jcheck.so
+tests/native/libb2jcheck.so: tests/native/mathcheck.cpp $(CSRC)/b2j_math.h $(CSRC)/huff_lut.cpp $(CSRC)/b2j_internal.h
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -I$(CSRC) -Iinclude tests/native/mathcheck.cpp $(CSRC)/huff_lut.cpp -o $@
+
+oracle:
+	$(MAKE) -s -C oracle all
+
+clean:
+	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) tests/native/*.so
+	$(MAKE) -s -C oracle clean
+
+.PHONY: all oracle clean mathcheck

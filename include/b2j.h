@@ -1,0 +1,186 @@
+/*
+ * b2j.h -- C ABI of the B200-native baseline-JPEG decode path.
+ *
+ * This is the drop-in boundary for the hot path of xinfushe/oclJPEGDecoder
+ * (entropy decode -> dequant/IDCT -> chroma upsample + YCbCr->BGRA). Plain pointers and
+ * sizes only; no C++ or torch types. Everything behind it is hand-written CUDA for sm_100a.
+ * There is no CPU fallback: every entry point that needs the device fails with
+ * B2J_E_NODEVICE / B2J_E_CUDA when no B200 is usable.
+ *
+ * Which reference interface each entry point replaces (paths relative to the reference repo):
+ *
+ *   b2j_parse_header        parser.cpp:272-372  load_jpg() up to and including SOS, with the
+ *                                               segment readers read_soi/dqt/sof/dht/dri/sos
+ *                                               (parser.cpp:7-270) and the accept gate
+ *                                               is_supported_file() (decoder.h:4, decoder.cpp:18-70)
+ *                                               and the geometry of decode_init() (decoder.cpp:161-199)
+ *   b2j_create/destroy      idct.h:9-10,18      Initialize_OpenCL_IDCT(), clidct_create(),
+ *                                               clidct_clean_up() (oclDCT8x8.cpp:25-110,306-341)
+ *   b2j_batch_create        idct.h:11-12        clidct_allocate_memory() + the host->device
+ *                                               transfer (oclDCT8x8.cpp:112-165); here the
+ *                                               COMPRESSED scan is uploaded, not coefficients
+ *   b2j_batch_decode        decoder.h:6-7       decode_huffman_data() + decode_mcu_data()
+ *                                               (decoder.cpp:262-365, 397-523) and clidct_run()
+ *                                               (idct.h:14, oclDCT8x8.cpp:275-299)
+ *   b2j_batch_sync          idct.h:17           clidct_wait_for_completion()
+ *   b2j_batch_read_pixels   idct.h:16           clidct_retrieve_image_from_device() (tight pitch W*4)
+ *   b2j_batch_read_coefs    idct.h:15           clidct_retrieve_data_from_device(): int32[blk][64],
+ *                                               natural order, dequantised == JPG_DATA::mcu_data
+ *                                               after decode_huffman_data() (jpeg.h:74)
+ *   b2j_decode_host         parser.cpp:376-397  the whole per-file sequence, batched, host buffers
+ *                                               in and out
+ *
+ * The C++ shim that keeps the reference's own four decoder.h signatures on top of this ABI is
+ * ocljpegdecoder_b200/csrc/refshim/; INTEGRATION.md shows the binding.
+ */
+#ifndef B2J_H_INCLUDED
+#define B2J_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2J_ABI_VERSION 1
+
+/* ---- return codes (0 = success, like the reference's `true`) ---- */
+#define B2J_OK 0
+#define B2J_E_ARG (-1)         /* bad argument                                              */
+#define B2J_E_FORMAT (-2)      /* container malformed; the reference would stop parsing     */
+#define B2J_E_UNSUPPORTED (-3) /* rejected by the accept gate                               */
+#define B2J_E_DATA (-4)        /* entropy-coded data corrupt (see per-image status bits)    */
+#define B2J_E_NOMEM (-5)
+#define B2J_E_CUDA (-6)        /* a CUDA call failed; b2j_last_error() has the text         */
+#define B2J_E_NODEVICE (-7)    /* no usable sm_100 device: there is no CPU fallback         */
+
+/* ---- per-image status bits written by the kernels (0 = clean decode) ---- */
+#define B2J_ST_BAD_CODE 0x01      /* bit pattern is no codeword (huffman.h:304-308)          */
+#define B2J_ST_RST_MISMATCH 0x02  /* RSTn out of sequence or missing (decoder.cpp:298-302)   */
+#define B2J_ST_OVERRUN 0x04       /* decode ran past its data (decoder.cpp:310-314)          */
+#define B2J_ST_BLOCK_OVERFLOW 0x08 /* more than 64 coefficients in a block (decoder.cpp:259) */
+#define B2J_ST_DC_RANGE 0x10      /* DC category > 16 or DC predictor outside int16          */
+#define B2J_ST_SEGMENT_END 0x20   /* a restart interval did not end at its marker            */
+
+/* ---- accept gate ---- */
+#define B2J_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: 4:2:0 (22,11,11) and 4:4:4        */
+#define B2J_GATE_EXTENDED 1  /* + 4:2:2 (21,11,11) and 4:4:0 (12,11,11), BASELINE config 4   */
+
+/* reference enum ColorSpace (macro.h:114-119) */
+#define B2J_CS_YUV444 0
+#define B2J_CS_YUV411 1
+#define B2J_CS_OTHER 2
+
+/* Parsed frame/scan header of one baseline JPEG: the POD equivalent of the reference's
+ * JPG_DATA (jpeg.h:59-81) minus the pointers. Quantisation tables stay in file (zig-zag)
+ * order like parser.cpp:65-86 keeps them; Huffman tables are kept as the DHT payload
+ * (16 counts + symbols), slot = Tc*4 + Th (Tc 0 = DC, 1 = AC; Th 0..3). */
+typedef struct b2j_image_desc
+{
+    int32_t width, height;
+    uint8_t sampling[3];  /* (h<<4)|v per component, SOF0                                   */
+    uint8_t quant_id[3];
+    uint8_t huff_id[3];   /* (Td<<4)|Ta per component, SOS                                  */
+    uint8_t color_space;  /* B2J_CS_*                                                       */
+    uint8_t quant_present[4];
+    uint8_t huff_present[8];
+    int32_t restart_interval;
+    int32_t mcu_width, mcu_height;         /* pixels                                        */
+    int32_t mcu_count_w, mcu_count_h, mcu_count;
+    int32_t blks_per_mcu[3];
+    int32_t tot_blks_per_mcu;
+    int32_t blk_count;
+    uint64_t scan_offset;                  /* first entropy-coded byte                      */
+    uint64_t scan_size;                    /* bytes from scan_offset to the end of the file */
+    uint16_t quant[4][64];
+    uint8_t huff_counts[8][16];
+    uint8_t huff_symbols[8][256];
+} b2j_image_desc;
+
+typedef struct b2j_ctx b2j_ctx;
+typedef struct b2j_batch b2j_batch;
+
+/* Byte/launch accounting of one b2j_batch_decode() (for the roofline arithmetic). */
+typedef struct b2j_batch_info
+{
+    int32_t n_images;
+    int32_t kernel_launches;      /* kernels enqueued by one b2j_batch_decode()             */
+    int64_t total_pixels;         /* sum W*H                                                */
+    int64_t total_blocks;         /* sum blk_count (padding MCUs included)                  */
+    int64_t scan_bytes;           /* sum of entropy-coded bytes uploaded                    */
+    int64_t coef_plane_bytes;     /* 128 * total_blocks                                     */
+    int64_t pixel_bytes;          /* 4 * total_pixels                                       */
+    int64_t algorithmic_bytes;    /* scan + 2*coef_plane + pixel             */
+    int64_t device_bytes;         /* device memory held by the batch                        */
+    int64_t h2d_bytes;            /* bytes b2j_batch_upload() copies                        */
+} b2j_batch_info;
+
+/* Device timings of the stages of the most recent b2j_batch_decode_timed(), milliseconds. */
+typedef struct b2j_stage_times
+{
+    float prepass_ms;   /* marker scan + unstuff + restart-interval table                   */
+    float huffman_ms;   /* entropy decode -> int16 coefficient plane                        */
+    float idct_ms;      /* dequant + IDCT + upsample + colour -> BGRA                       */
+    float total_ms;
+} b2j_stage_times;
+
+/* ------------------------------------------------------------------ host-only ---------- */
+int b2j_abi_version(void);
+const char *b2j_strerror(int code);
+/* Text of the last CUDA/runtime failure on this thread ("" when none). */
+const char *b2j_last_error(void);
+
+/* Parse SOI .. SOS of a baseline JFIF file held in memory. Same accept/reject behaviour as
+ * the reference's load_jpg() + is_supported_file() (gate = B2J_GATE_REFERENCE), or with
+ * 4:2:2 / 4:4:0 admitted (B2J_GATE_EXTENDED). */
+int b2j_parse_header(const uint8_t *file, size_t len, int gate, b2j_image_desc *out);
+
+/* ------------------------------------------------------------------ device -------------- */
+int b2j_device_count(void);
+int b2j_create(int device, b2j_ctx **out);
+void b2j_destroy(b2j_ctx *ctx);
+
+/* Build a batch: stages the entropy-coded bytes of every image (files[i] + desc.scan_offset)
+ * in pinned host memory, builds the decode tables, allocates all device buffers. Nothing is
+ * copied to the device yet. */
+int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs, const uint8_t *const *files,
+                     const size_t *lens, b2j_batch **out);
+void b2j_batch_destroy(b2j_batch *batch);
+int b2j_batch_get_info(const b2j_batch *batch, b2j_batch_info *info);
+
+/* stream: a cudaStream_t passed as void* (NULL = the context's own stream). All calls below
+ * only enqueue work unless stated. */
+int b2j_batch_upload(b2j_batch *batch, void *stream);   /* H2D: scan bytes + tables        */
+int b2j_batch_decode(b2j_batch *batch, void *stream);   /* the hot path, device resident   */
+/* Same as b2j_batch_decode() with CUDA events between the stages; synchronises. */
+int b2j_batch_decode_timed(b2j_batch *batch, void *stream, b2j_stage_times *times);
+int b2j_batch_sync(b2j_batch *batch, void *stream);
+
+/* Per-image status words (B2J_ST_* bits). Synchronises the stream. */
+int b2j_batch_status(b2j_batch *batch, void *stream, int32_t *status /* n */);
+
+/* Device-resident results. Pixels: BGRA (A = 0), top-down, tight pitch width*4. */
+int b2j_batch_pixels_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes);
+/* Coefficient plane: int16[blk_count][64], natural order, QUANTISED (dequantisation happens
+ * at IDCT load), MCU-interleaved block order. */
+int b2j_batch_coefs_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes);
+
+/* D2H of one image (synchronises). dst: width*height*4 bytes. */
+int b2j_batch_read_pixels(b2j_batch *batch, void *stream, int image, uint8_t *dst);
+/* D2H of every image into dsts[i] (pinned staging, one copy per image; synchronises). */
+int b2j_batch_read_all_pixels(b2j_batch *batch, void *stream, uint8_t *const *dsts);
+/* The reference's coefficient tap: int32[blk_count][64], natural order, dequantised on the
+ * device by a small expansion kernel, then copied (synchronises). */
+int b2j_batch_read_coefs(b2j_batch *batch, void *stream, int image, int32_t *dst);
+
+/* Whole path with host buffers in and out: parse, upload, decode, download.
+ * out_bgra[i] must hold width*height*4 bytes (use b2j_parse_header() to size it); images whose
+ * header is rejected get status[i] = the negative B2J_E_* code and are skipped. */
+int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, int gate,
+                    uint8_t *const *out_bgra, int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2J_H_INCLUDED */

@@ -1,0 +1,239 @@
+"""ctypes bindings of include/b2j.h (one Python method per C entry point)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+GATE_REFERENCE = 0
+GATE_EXTENDED = 1
+
+B2J_OK = 0
+B2J_E_NODEVICE = -7
+
+# every symbol include/b2j.h declares (tests check that the built library exports all of them)
+EXPORTED_SYMBOLS = [
+    "b2j_abi_version", "b2j_strerror", "b2j_last_error", "b2j_parse_header", "b2j_device_count",
+    "b2j_create", "b2j_destroy", "b2j_batch_create", "b2j_batch_destroy", "b2j_batch_get_info",
+    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_sync", "b2j_batch_status",
+    "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
+    "b2j_batch_read_coefs", "b2j_decode_host",
+]
+
+
+class B2JError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__("%s failed: %d%s" % (where, code, (" (" + detail + ")") if detail else ""))
+
+
+class ImageDesc(ctypes.Structure):
+    """b2j_image_desc"""
+    _fields_ = [
+        ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+        ("sampling", ctypes.c_uint8 * 3), ("quant_id", ctypes.c_uint8 * 3), ("huff_id", ctypes.c_uint8 * 3),
+        ("color_space", ctypes.c_uint8),
+        ("quant_present", ctypes.c_uint8 * 4), ("huff_present", ctypes.c_uint8 * 8),
+        ("restart_interval", ctypes.c_int32),
+        ("mcu_width", ctypes.c_int32), ("mcu_height", ctypes.c_int32),
+        ("mcu_count_w", ctypes.c_int32), ("mcu_count_h", ctypes.c_int32), ("mcu_count", ctypes.c_int32),
+        ("blks_per_mcu", ctypes.c_int32 * 3), ("tot_blks_per_mcu", ctypes.c_int32), ("blk_count", ctypes.c_int32),
+        ("scan_offset", ctypes.c_uint64), ("scan_size", ctypes.c_uint64),
+        ("quant", (ctypes.c_uint16 * 64) * 4),
+        ("huff_counts", (ctypes.c_uint8 * 16) * 8),
+        ("huff_symbols", (ctypes.c_uint8 * 256) * 8),
+    ]
+
+
+class BatchInfo(ctypes.Structure):
+    """b2j_batch_info"""
+    _fields_ = [
+        ("n_images", ctypes.c_int32), ("kernel_launches", ctypes.c_int32),
+        ("total_pixels", ctypes.c_int64), ("total_blocks", ctypes.c_int64), ("scan_bytes", ctypes.c_int64),
+        ("coef_plane_bytes", ctypes.c_int64), ("pixel_bytes", ctypes.c_int64), ("algorithmic_bytes", ctypes.c_int64),
+        ("device_bytes", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
+    ]
+
+
+class StageTimes(ctypes.Structure):
+    """b2j_stage_times"""
+    _fields_ = [("prepass_ms", ctypes.c_float), ("huffman_ms", ctypes.c_float), ("idct_ms", ctypes.c_float),
+                ("total_ms", ctypes.c_float)]
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libb2j.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads lib/libb2j.so. There is no fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.isfile(path):
+        raise ImportError("%s not built; run `make` or __graft_entry__.build() (there is no CPU fallback)" % path)
+    L = ctypes.CDLL(path)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.b2j_abi_version.restype = ci
+    L.b2j_strerror.restype = ctypes.c_char_p
+    L.b2j_strerror.argtypes = [ci]
+    L.b2j_last_error.restype = ctypes.c_char_p
+    L.b2j_parse_header.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ci, ctypes.POINTER(ImageDesc)]
+    L.b2j_device_count.restype = ci
+    L.b2j_create.argtypes = [ci, ctypes.POINTER(vp)]
+    L.b2j_destroy.argtypes = [vp]
+    L.b2j_destroy.restype = None
+    L.b2j_batch_create.argtypes = [vp, ci, ctypes.POINTER(ImageDesc), ctypes.POINTER(ctypes.c_char_p),
+                                   ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(vp)]
+    L.b2j_batch_destroy.argtypes = [vp]
+    L.b2j_batch_destroy.restype = None
+    L.b2j_batch_get_info.argtypes = [vp, ctypes.POINTER(BatchInfo)]
+    L.b2j_batch_upload.argtypes = [vp, vp]
+    L.b2j_batch_decode.argtypes = [vp, vp]
+    L.b2j_batch_decode_timed.argtypes = [vp, vp, ctypes.POINTER(StageTimes)]
+    L.b2j_batch_sync.argtypes = [vp, vp]
+    L.b2j_batch_status.argtypes = [vp, vp, vp]
+    L.b2j_batch_pixels_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.b2j_batch_coefs_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.b2j_batch_read_pixels.argtypes = [vp, vp, ci, vp]
+    L.b2j_batch_read_all_pixels.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    L.b2j_batch_read_coefs.argtypes = [vp, vp, ci, vp]
+    L.b2j_decode_host.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t), ci,
+                                  ctypes.POINTER(vp), vp]
+    _LIB = L
+    return L
+
+
+def _check(rc, where):
+    if rc != B2J_OK:
+        L = load_library()
+        raise B2JError(rc, where, (L.b2j_strerror(rc) or b"").decode() + "; " + (L.b2j_last_error() or b"").decode())
+
+
+def parse_header(data, gate=GATE_EXTENDED):
+    """b2j_parse_header: returns (rc, ImageDesc). rc != 0 means the file is refused."""
+    L = load_library()
+    d = ImageDesc()
+    rc = L.b2j_parse_header(data, len(data), gate, ctypes.byref(d))
+    return rc, d
+
+
+class Decoder:
+    """b2j_ctx: one per GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self._h = ctypes.c_void_p()
+        _check(self.lib.b2j_create(device, ctypes.byref(self._h)), "b2j_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self.lib.b2j_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def batch(self, files, gate=GATE_EXTENDED):
+        """Parse + b2j_batch_create for a list of bytes objects (all must pass the gate)."""
+        descs = (ImageDesc * len(files))()
+        for i, f in enumerate(files):
+            rc = self.lib.b2j_parse_header(f, len(f), gate, ctypes.byref(descs[i]))
+            _check(rc, "b2j_parse_header[%d]" % i)
+        return Batch(self, files, descs)
+
+    def decode_host(self, files, outs=None, gate=GATE_EXTENDED):
+        """b2j_decode_host: host bytes in, host BGRA arrays out. Returns (outs, status)."""
+        n = len(files)
+        if outs is None:
+            outs = []
+            for f in files:
+                rc, d = parse_header(f, gate)
+                outs.append(np.zeros((d.height, d.width, 4), np.uint8) if rc == 0 else np.zeros((0, 0, 4), np.uint8))
+        fp = (ctypes.c_char_p * n)(*files)
+        ln = (ctypes.c_size_t * n)(*[len(f) for f in files])
+        op = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        status = np.zeros(n, np.int32)
+        _check(self.lib.b2j_decode_host(self._h, n, fp, ln, gate, op, status.ctypes.data), "b2j_decode_host")
+        return outs, status
+
+
+class Batch:
+    """b2j_batch: a set of images resident on one GPU."""
+
+    def __init__(self, dec, files, descs):
+        self.dec = dec
+        self.lib = dec.lib
+        self.files = list(files)   # keep the bytes alive
+        self.descs = descs
+        self.n = len(files)
+        fp = (ctypes.c_char_p * self.n)(*self.files)
+        ln = (ctypes.c_size_t * self.n)(*[len(f) for f in self.files])
+        self._h = ctypes.c_void_p()
+        _check(self.lib.b2j_batch_create(dec._h, self.n, descs, fp, ln, ctypes.byref(self._h)), "b2j_batch_create")
+
+    def close(self):
+        if self._h:
+            self.lib.b2j_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        inf = BatchInfo()
+        _check(self.lib.b2j_batch_get_info(self._h, ctypes.byref(inf)), "b2j_batch_get_info")
+        return inf
+
+    def upload(self, stream=None):
+        _check(self.lib.b2j_batch_upload(self._h, stream), "b2j_batch_upload")
+
+    def decode(self, stream=None):
+        _check(self.lib.b2j_batch_decode(self._h, stream), "b2j_batch_decode")
+
+    def decode_timed(self, stream=None):
+        t = StageTimes()
+        _check(self.lib.b2j_batch_decode_timed(self._h, stream, ctypes.byref(t)), "b2j_batch_decode_timed")
+        return t
+
+    def sync(self, stream=None):
+        _check(self.lib.b2j_batch_sync(self._h, stream), "b2j_batch_sync")
+
+    def status(self, stream=None):
+        st = np.zeros(self.n, np.int32)
+        _check(self.lib.b2j_batch_status(self._h, stream, st.ctypes.data), "b2j_batch_status")
+        return st
+
+    def pixels(self, i, stream=None):
+        d = self.descs[i]
+        out = np.zeros((d.height, d.width, 4), np.uint8)
+        _check(self.lib.b2j_batch_read_pixels(self._h, stream, i, out.ctypes.data), "b2j_batch_read_pixels")
+        return out
+
+    def read_all_pixels(self, outs, stream=None):
+        op = (ctypes.c_void_p * self.n)(*[o if isinstance(o, int) else o.ctypes.data for o in outs])
+        _check(self.lib.b2j_batch_read_all_pixels(self._h, stream, op), "b2j_batch_read_all_pixels")
+
+    def coefs(self, i, stream=None):
+        """The reference's coefficient tap: int32 [blk_count, 64], natural order, dequantised."""
+        d = self.descs[i]
+        out = np.zeros((d.blk_count, 64), np.int32)
+        _check(self.lib.b2j_batch_read_coefs(self._h, stream, i, out.ctypes.data), "b2j_batch_read_coefs")
+        return out
+
+    def pixels_device(self, i):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self.lib.b2j_batch_pixels_device(self._h, i, ctypes.byref(p), ctypes.byref(n)), "b2j_batch_pixels_device")
+        return p.value, n.value

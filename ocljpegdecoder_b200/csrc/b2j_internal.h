@@ -1,0 +1,73 @@
+// b2j_internal.h -- data layout shared by the host runtime and the kernels (not part of the ABI).
+#ifndef B2J_INTERNAL_H_INCLUDED
+#define B2J_INTERNAL_H_INCLUDED
+
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+
+#include "../../include/b2j.h"
+
+namespace b2j {
+
+// ---------------------------------------------------------------- constants ------------
+constexpr int kScanChunkBytes = 4096;    // bytes of raw scan one CTA of the pre-pass handles
+constexpr int kScanThreads = 256;        // 16 bytes per thread
+constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
+constexpr int kLutBits = 10;             // primary Huffman LUT width
+constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set
+constexpr int kLutMaxEntries = 12288;    // u16 entries of one LUT set (24 KB of shared memory)
+constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
+constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
+constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
+constexpr uint32_t kNoTerm = 0xFFFFu;
+
+// LUT entry (u16):
+//   leaf   : bit15 = 0; bits 0-4 code length (1..16, 0 = no codeword has this prefix);
+//            bits 5-9 value-bit count (AC: size nibble; DC: category); bits 10-13 zero run
+//   escape : bit15 = 1; bits 0-3 extra index bits nb (1..16-kLutBits);
+//            bits 4-14 sub-table offset relative to the end of the primary table
+constexpr uint16_t kLutEscape = 0x8000;
+
+// sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)
+enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3 };
+
+// Per-image record in device memory.
+struct ImgDev
+{
+    uint64_t raw_off;      // byte offset of the scan in raw[] and of the clean stream in clean[] (16 B aligned)
+    uint64_t pix_off;      // byte offset of the BGRA image in pixels[] (256 B aligned)
+    uint32_t raw_len;      // entropy-coded bytes (to the end of the file)
+    uint32_t chunk_first;  // first pre-pass chunk of this image
+    uint32_t n_chunks;
+    uint32_t seg_first;    // first decode segment (restart interval) of this image
+    uint32_t n_segs;
+    uint32_t blk_first;    // first row of this image in the coefficient plane
+    uint32_t blk_count;
+    uint32_t mcu_count;
+    uint32_t mcu_count_w;
+    uint32_t restart_interval; // MCUs per segment (== mcu_count when the file has no DRI)
+    uint32_t has_dri;
+    uint32_t width, height;
+    uint32_t lut_off;      // u16 offset of the LUT set in luts[]
+    uint32_t lut_len;      // u16 length of the LUT set (header included)
+    uint32_t mode;         // SamplingMode
+    uint32_t tot_blks;     // blocks per MCU
+    uint32_t ny_blks;      // luma blocks per MCU
+    uint32_t yh;           // luma blocks per MCU row
+    uint32_t wide_q;       // 1 when some quantiser value exceeds 255
+};
+
+struct HuffCtaDev { uint32_t img; uint32_t seg_first; };   // segment index local to the image
+struct TileDev { uint32_t img; uint32_t mcu_first; };
+
+// ---------------------------------------------------------------- host helpers ---------
+// Canonical Huffman table -> two-level LUT. Returns false when the table cannot be built
+// (code space overflow) or needs more than `max_entries` entries.
+bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out, size_t max_entries);
+
+// LUT set for one image: header (offsets of the DC/AC table of each component) + tables.
+bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out);
+
+} // namespace b2j
+#endif

@@ -1,0 +1,121 @@
+// huff_lut.cpp -- host-side construction of the Huffman decode tables the kernels use.
+//
+// The reference decodes with a 16-ary trie walked 4 bits at a time (huffman.h:200-314, built at
+// decoder.cpp:266-273 from the ASCII code strings of parser.cpp:221-257). On the GPU a symbol is
+// one shared-memory lookup: the next kLutBits bits index a primary table whose entry carries
+// code length, value-bit count and zero run; the rare longer codes take one more lookup in a
+// sub-table addressed by the remaining bits. Both are prefix-code decoders of the same canonical
+// code, so they accept and reject exactly the same bit strings.
+#include "b2j_internal.h"
+
+#include <string.h>
+
+namespace b2j {
+
+namespace {
+inline uint16_t leaf_entry(int len, int sym, bool is_dc)
+{
+    int size, run;
+    if (is_dc) { size = sym; run = 0; if (size > 16) return 0; }   // category > 16: not decodable here
+    else { size = sym & 15; run = sym >> 4; }
+    return (uint16_t)(len | (size << 5) | (run << 10));
+}
+} // namespace
+
+bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out, size_t max_entries)
+{
+    constexpr int K = kLutBits;
+    struct Code { uint32_t code; int len; int sym; };
+    Code codes[256];
+    int n = 0;
+    uint32_t code = 0;
+    for (int l = 1; l <= 16; l++)
+    {
+        for (int i = 0; i < counts[l - 1]; i++)
+        {
+            if (n >= 256 || (code >> l)) return false;   // parser.cpp:239 "invalid tree"
+            codes[n].code = code; codes[n].len = l; codes[n].sym = symbols[n];
+            n++; code++;
+        }
+        code <<= 1;
+    }
+    out.assign((size_t)1 << K, 0);
+    // longest code below each K-bit prefix
+    std::vector<uint8_t> maxlen((size_t)1 << K, 0);
+    for (int i = 0; i < n; i++)
+    {
+        const Code &c = codes[i];
+        if (c.len <= K)
+        {
+            const uint32_t first = c.code << (K - c.len), cnt = 1u << (K - c.len);
+            const uint16_t e = leaf_entry(c.len, c.sym, is_dc);
+            for (uint32_t k = 0; k < cnt; k++) out[first + k] = e;
+        }
+        else
+        {
+            const uint32_t prefix = c.code >> (c.len - K);
+            if (maxlen[prefix] < c.len) maxlen[prefix] = (uint8_t)c.len;
+        }
+    }
+    // one sub-table per prefix that has long codes
+    std::vector<uint32_t> sub_off((size_t)1 << K, 0);
+    for (uint32_t p = 0; p < (1u << K); p++)
+    {
+        if (!maxlen[p]) continue;
+        const int nb = maxlen[p] - K;
+        const size_t rel = out.size() - ((size_t)1 << K);
+        if (rel >= 2048) return false;
+        sub_off[p] = (uint32_t)out.size();
+        out[p] = (uint16_t)(kLutEscape | nb | (rel << 4));
+        out.resize(out.size() + ((size_t)1 << nb), 0);
+        if (out.size() > max_entries) return false;
+    }
+    for (int i = 0; i < n; i++)
+    {
+        const Code &c = codes[i];
+        if (c.len <= K) continue;
+        const uint32_t prefix = c.code >> (c.len - K);
+        const int nb = maxlen[prefix] - K, extra = c.len - K;
+        const uint32_t rem = c.code & ((1u << extra) - 1u);
+        const uint32_t first = rem << (nb - extra), cnt = 1u << (nb - extra);
+        const uint16_t e = leaf_entry(c.len, c.sym, is_dc);
+        for (uint32_t k = 0; k < cnt; k++) out[sub_off[prefix] + first + k] = e;
+    }
+    return out.size() <= max_entries;
+}
+
+bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out)
+{
+    out.assign(kLutHeader, 0);
+    int built_slot[8];
+    uint32_t built_off[8];
+    int nbuilt = 0;
+    for (int c = 0; c < 3; c++)
+    {
+        for (int kind = 0; kind < 2; kind++)   // 0 = DC, 1 = AC
+        {
+            const int th = kind == 0 ? (d.huff_id[c] >> 4) : (d.huff_id[c] & 0xF);
+            if (th > 3) return false;
+            const int slot = kind * 4 + th;
+            if (!d.huff_present[slot]) return false;
+            uint32_t off = 0;
+            bool found = false;
+            for (int k = 0; k < nbuilt; k++)
+                if (built_slot[k] == slot) { off = built_off[k]; found = true; }
+            if (!found)
+            {
+                std::vector<uint16_t> t;
+                if (!build_huff_lut(d.huff_counts[slot], d.huff_symbols[slot], kind == 0, t, kLutMaxEntries)) return false;
+                off = (uint32_t)out.size();
+                out.insert(out.end(), t.begin(), t.end());
+                built_slot[nbuilt] = slot; built_off[nbuilt] = off; nbuilt++;
+            }
+            if (off > 0xFFFF) return false;
+            out[kind * 3 + c] = (uint16_t)off;
+        }
+    }
+    while (out.size() & 7) out.push_back(0);   // 16-byte granules for the copy into shared memory
+    return out.size() <= (size_t)kLutMaxEntries;
+}
+
+} // namespace b2j

@@ -1,0 +1,46 @@
+// kernels.h -- host-callable launchers of kernels.cu.
+#ifndef B2J_KERNELS_H_INCLUDED
+#define B2J_KERNELS_H_INCLUDED
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2j_internal.h"
+
+namespace b2j {
+
+struct DecodeArgs
+{
+    // inputs
+    const uint8_t *raw;
+    const ImgDev *imgs;
+    const uint32_t *chunk_img;
+    const HuffCtaDev *huff_ctas;
+    const TileDev *tiles;
+    const uint16_t *luts;
+    const uint16_t *qtabs;
+    const CUtensorMap *tmap;   // host copy, passed by value to the kernel
+    // scratch
+    uint8_t *clean;
+    uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;
+    uint32_t *clean_len, *seg_start;
+    // outputs
+    int16_t *coef;
+    uint8_t *pixels;
+    int32_t *status;
+    // sizes
+    uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len;
+    bool use_tma;
+};
+
+cudaError_t init_constants();
+cudaError_t configure_kernels(uint32_t max_lut_len);
+size_t huff_smem_bytes(uint32_t max_lut_len);
+void launch_prepass(const DecodeArgs &a, cudaStream_t s);   // 3 kernels
+void launch_huffman(const DecodeArgs &a, cudaStream_t s);   // 1 kernel
+void launch_idct(const DecodeArgs &a, cudaStream_t s);      // 1 kernel
+void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s);
+
+} // namespace b2j
+#endif

@@ -1,0 +1,655 @@
+// runtime.cu -- the extern "C" layer: contexts, batches, uploads, launches, read-back.
+//
+// Replaces the reference's OpenCL host runtime (oclDCT8x8.cpp:25-341: device discovery,
+// context/queue, buffers, blocking transfers, run-time program build, launch, teardown) with a
+// CUDA runtime layer in which whole batches of images stay resident on one B200:
+//   b2j_batch_create   lays out every buffer of a batch once (compressed scans, tables, segment
+//                      and tile descriptors, coefficient plane, pixel plane)
+//   b2j_batch_upload   one host->device copy of the packed input blob
+//   b2j_batch_decode   5 kernel launches on one stream, no host synchronisation
+// There is no CPU fallback anywhere in this file: without a device every call fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2j_internal.h"
+#include "b2j_math.h"
+#include "kernels.h"
+
+using namespace b2j;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+int fail_cuda(cudaError_t e, const char *what)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    t_last_error = buf;
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? B2J_E_NODEVICE : B2J_E_CUDA;
+}
+
+#define CU_TRY(expr)                                              \
+    do {                                                          \
+        cudaError_t e__ = (expr);                                 \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #expr);     \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// A grow-only cache of device / pinned allocations so that repeated batches (the e2e path) do
+// not pay cudaMalloc / cudaHostAlloc every call.
+struct Pool
+{
+    struct Buf { void *p; size_t cap; };
+    std::vector<Buf> free_list;
+    bool pinned;
+    explicit Pool(bool pin) : pinned(pin) {}
+    cudaError_t get(size_t n, void **out, size_t *cap)
+    {
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].cap >= n && (best == (size_t)-1 || free_list[i].cap < free_list[best].cap)) best = i;
+        if (best != (size_t)-1)
+        {
+            *out = free_list[best].p; *cap = free_list[best].cap;
+            free_list.erase(free_list.begin() + (long)best);
+            return cudaSuccess;
+        }
+        n = align_up(n ? n : 1, 1 << 20);
+        cudaError_t e = pinned ? cudaHostAlloc(out, n, cudaHostAllocDefault) : cudaMalloc(out, n);
+        *cap = n;
+        return e;
+    }
+    void put(void *p, size_t cap) { if (p) free_list.push_back({p, cap}); }
+    void drain()
+    {
+        for (auto &b : free_list) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+        free_list.clear();
+    }
+};
+
+} // namespace
+
+struct b2j_ctx
+{
+    int device;
+    cudaStream_t stream;
+    PFN_cuTensorMapEncodeTiled_v12000 encode_tiled;
+    bool use_tma;
+    Pool dev_pool{false};
+    Pool pin_pool{true};
+    std::mutex mu;
+};
+
+struct b2j_batch
+{
+    b2j_ctx *ctx;
+    int n;
+    std::vector<b2j_image_desc> descs;
+    std::vector<ImgDev> imgs;
+    b2j_batch_info info;
+
+    // packed input blob: host (pinned) and device copies share one layout
+    uint8_t *h_blob; size_t h_blob_cap;
+    uint8_t *d_blob; size_t d_blob_cap;
+    size_t blob_bytes;
+    size_t off_imgs, off_chunk_img, off_ctas, off_tiles, off_luts, off_qtabs, off_raw;
+
+    // scratch + outputs
+    uint8_t *d_scratch; size_t d_scratch_cap;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status;
+    size_t scratch_bytes;
+    int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
+    uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
+    int32_t *d_expand; size_t d_expand_cap;   // lazily allocated for the coefficient tap
+
+    CUtensorMap tmap;
+    DecodeArgs args;
+    uint32_t n_segs_total;
+    bool uploaded;
+};
+
+namespace {
+
+int make_tensor_map(b2j_ctx *ctx, b2j_batch *b)
+{
+    memset(&b->tmap, 0, sizeof(b->tmap));
+    if (!ctx->encode_tiled) return B2J_OK;
+    // coefficient plane as a 2-D tensor [rows][64] of int16; box = one tile, 128-byte swizzle
+    const cuuint64_t dims[2] = {64, (cuuint64_t)b->coef_rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTileBlocks};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(&b->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, b->d_coef, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+        t_last_error = buf;
+        return B2J_E_CUDA;
+    }
+    return B2J_OK;
+}
+
+uint32_t mode_of(const b2j_image_desc &d)
+{
+    switch (d.sampling[0])
+    {
+    case 0x11: return kMode444;
+    case 0x22: return kMode420;
+    case 0x21: return kMode422;
+    default: return kMode440;
+    }
+}
+
+cudaStream_t pick_stream(const b2j_batch *b, void *stream) { return stream ? (cudaStream_t)stream : b->ctx->stream; }
+
+void release_batch_buffers(b2j_batch *b)
+{
+    b2j_ctx *c = b->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->pin_pool.put(b->h_blob, b->h_blob_cap);
+    c->dev_pool.put(b->d_blob, b->d_blob_cap);
+    c->dev_pool.put(b->d_scratch, b->d_scratch_cap);
+    c->dev_pool.put(b->d_coef, b->d_coef_cap);
+    c->dev_pool.put(b->d_pix, b->d_pix_cap);
+    c->dev_pool.put(b->d_expand, b->d_expand_cap);
+    b->h_blob = b->d_blob = b->d_scratch = b->d_pix = nullptr;
+    b->d_coef = nullptr; b->d_expand = nullptr;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+extern "C" int b2j_abi_version(void) { return B2J_ABI_VERSION; }
+
+extern "C" const char *b2j_strerror(int code)
+{
+    switch (code)
+    {
+    case B2J_OK: return "ok";
+    case B2J_E_ARG: return "bad argument";
+    case B2J_E_FORMAT: return "malformed or unsupported container";
+    case B2J_E_UNSUPPORTED: return "rejected by the accept gate";
+    case B2J_E_DATA: return "corrupt entropy-coded data";
+    case B2J_E_NOMEM: return "out of memory";
+    case B2J_E_CUDA: return "CUDA failure";
+    case B2J_E_NODEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    default: return "unknown";
+    }
+}
+
+extern "C" const char *b2j_last_error(void) { return t_last_error.c_str(); }
+
+extern "C" int b2j_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b2j_create(int device, b2j_ctx **out)
+{
+    if (!out) return B2J_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+    {
+        cudaGetLastError();
+        t_last_error = "no CUDA device visible; this library has no CPU fallback";
+        return B2J_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        t_last_error = std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only";
+        return B2J_E_NODEVICE;
+    }
+    b2j_ctx *ctx = new b2j_ctx;
+    ctx->device = device;
+    ctx->encode_tiled = nullptr;
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(init_constants());
+    CU_TRY(configure_kernels(kLutMaxEntries));
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    else
+        cudaGetLastError();
+    const char *env = getenv("B2J_USE_TMA");
+    ctx->use_tma = ctx->encode_tiled != nullptr && !(env && env[0] == '0');
+    *out = ctx;
+    return B2J_OK;
+}
+
+extern "C" void b2j_destroy(b2j_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->dev_pool.drain();
+    ctx->pin_pool.drain();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs, const uint8_t *const *files,
+                                const size_t *lens, b2j_batch **out)
+{
+    if (!ctx || n <= 0 || !descs || !files || !lens || !out) return B2J_E_ARG;
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(ctx->device));
+
+    b2j_batch *b = new b2j_batch();
+    b->ctx = ctx;
+    b->n = n;
+    b->descs.assign(descs, descs + n);
+    b->imgs.resize((size_t)n);
+    b->h_blob = b->d_blob = b->d_scratch = b->d_pix = nullptr;
+    b->d_coef = nullptr; b->d_expand = nullptr;
+    b->h_blob_cap = b->d_blob_cap = b->d_scratch_cap = b->d_coef_cap = b->d_pix_cap = b->d_expand_cap = 0;
+    b->uploaded = false;
+
+    std::vector<uint32_t> chunk_img;
+    std::vector<HuffCtaDev> ctas;
+    std::vector<TileDev> tiles;
+    std::vector<uint16_t> luts;
+    std::vector<uint16_t> qtabs((size_t)n * 192);
+    std::map<std::string, std::pair<uint32_t, uint32_t>> lut_cache;
+    static const uint8_t zz[64] = B2J_ZIGZAG_TABLE;
+
+    size_t raw_total = 0, pix_total = 0, blk_total = 0;
+    uint32_t seg_total = 0, max_lut_len = 0;
+    int64_t pixels = 0, scan_bytes = 0;
+    int rc = B2J_OK;
+    for (int i = 0; i < n && rc == B2J_OK; i++)
+    {
+        const b2j_image_desc &d = descs[i];
+        ImgDev &im = b->imgs[(size_t)i];
+        memset(&im, 0, sizeof(im));
+        if (d.width <= 0 || d.height <= 0 || d.mcu_count <= 0 || d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset ||
+            d.scan_size >= 0xFFFF0000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
+        { rc = B2J_E_ARG; break; }
+        im.raw_off = raw_total;
+        im.raw_len = (uint32_t)d.scan_size;
+        raw_total += align_up((size_t)im.raw_len + 32, 16);
+        im.pix_off = pix_total;
+        pix_total += align_up((size_t)d.width * d.height * 4, 256);
+        im.chunk_first = (uint32_t)chunk_img.size();
+        im.n_chunks = (im.raw_len + kScanChunkBytes - 1) / kScanChunkBytes;
+        for (uint32_t k = 0; k < im.n_chunks; k++) chunk_img.push_back((uint32_t)i);
+        im.mcu_count = (uint32_t)d.mcu_count;
+        im.mcu_count_w = (uint32_t)d.mcu_count_w;
+        im.has_dri = d.restart_interval > 0 ? 1u : 0u;
+        im.restart_interval = im.has_dri ? (uint32_t)d.restart_interval : im.mcu_count;
+        im.seg_first = seg_total;
+        im.n_segs = (im.mcu_count + im.restart_interval - 1) / im.restart_interval;
+        seg_total += im.n_segs;
+        for (uint32_t s = 0; s < im.n_segs; s += kHuffThreads) ctas.push_back({(uint32_t)i, s});
+        im.blk_first = (uint32_t)blk_total;
+        im.blk_count = (uint32_t)d.blk_count;
+        blk_total += (size_t)d.blk_count;
+        im.width = (uint32_t)d.width;
+        im.height = (uint32_t)d.height;
+        im.mode = mode_of(d);
+        im.tot_blks = (uint32_t)d.tot_blks_per_mcu;
+        im.ny_blks = (uint32_t)d.blks_per_mcu[0];
+        im.yh = (uint32_t)(d.sampling[0] >> 4);
+        const uint32_t mcus_per_tile = kTileBlocks / im.tot_blks;
+        for (uint32_t m = 0; m < im.mcu_count; m += mcus_per_tile) tiles.push_back({(uint32_t)i, m});
+        // quantisers: file (zig-zag) order -> natural order, per component (decoder.cpp:315,340)
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 64; k++)
+            {
+                const uint16_t q = d.quant[d.quant_id[c]][k];
+                qtabs[(size_t)i * 192 + (size_t)c * 64 + zz[k]] = q;
+                if (q > 255) im.wide_q = 1;
+            }
+        // decode tables, shared between images that carry identical DHT payloads
+        std::string key;
+        for (int c = 0; c < 3; c++)
+        {
+            const int slots[2] = {d.huff_id[c] >> 4, 4 + (d.huff_id[c] & 0xF)};
+            for (int s = 0; s < 2; s++)
+            {
+                if (slots[s] < 0 || slots[s] > 7 || !d.huff_present[slots[s]]) { rc = B2J_E_UNSUPPORTED; break; }
+                key.append((const char *)d.huff_counts[slots[s]], 16);
+                size_t tot = 0;
+                for (int l = 0; l < 16; l++) tot += d.huff_counts[slots[s]][l];
+                key.append((const char *)d.huff_symbols[slots[s]], tot);
+                key.push_back((char)0xA5);
+            }
+        }
+        if (rc != B2J_OK) break;
+        auto it = lut_cache.find(key);
+        if (it == lut_cache.end())
+        {
+            std::vector<uint16_t> set;
+            if (!build_lut_set(d, set)) { rc = B2J_E_UNSUPPORTED; t_last_error = "Huffman tables need more decode-table space than one CTA has"; break; }
+            const uint32_t off = (uint32_t)luts.size();
+            luts.insert(luts.end(), set.begin(), set.end());
+            it = lut_cache.emplace(key, std::make_pair(off, (uint32_t)set.size())).first;
+        }
+        im.lut_off = it->second.first;
+        im.lut_len = it->second.second;
+        if (im.lut_len > max_lut_len) max_lut_len = im.lut_len;
+        pixels += (int64_t)d.width * d.height;
+        scan_bytes += (int64_t)d.scan_size;
+    }
+    if (rc != B2J_OK) { delete b; return rc; }
+    if (blk_total + kTileBlocks >= 0xFFFFFFF0ull) { delete b; return B2J_E_ARG; }
+
+    // ---- input blob layout
+    size_t off = 0;
+    auto place = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    b->off_imgs = place(sizeof(ImgDev) * (size_t)n);
+    b->off_chunk_img = place(sizeof(uint32_t) * chunk_img.size());
+    b->off_ctas = place(sizeof(HuffCtaDev) * ctas.size());
+    b->off_tiles = place(sizeof(TileDev) * tiles.size());
+    b->off_luts = place(sizeof(uint16_t) * luts.size());
+    b->off_qtabs = place(sizeof(uint16_t) * qtabs.size());
+    b->off_raw = place(raw_total + 64);
+    b->blob_bytes = off;
+
+    // ---- scratch layout
+    off = 0;
+    b->off_clean = place(raw_total + 64);
+    b->off_chunk_cnt = place(4 * chunk_img.size());
+    b->off_chunk_term = place(4 * chunk_img.size());
+    b->off_chunk_bk = place(4 * chunk_img.size());
+    b->off_chunk_bm = place(4 * chunk_img.size());
+    b->off_clean_len = place(4 * (size_t)n);
+    b->off_seg_start = place(4 * (size_t)seg_total);
+    b->off_status = place(4 * (size_t)n);
+    b->scratch_bytes = off;
+    b->n_segs_total = seg_total;
+    b->coef_rows = blk_total + kTileBlocks;   // one tile of padding: the last tile may read past the last block
+    b->pix_bytes = pix_total;
+
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaError_t e;
+        if ((e = ctx->pin_pool.get(b->blob_bytes, (void **)&b->h_blob, &b->h_blob_cap)) != cudaSuccess ||
+            (e = ctx->dev_pool.get(b->blob_bytes, (void **)&b->d_blob, &b->d_blob_cap)) != cudaSuccess ||
+            (e = ctx->dev_pool.get(b->scratch_bytes, (void **)&b->d_scratch, &b->d_scratch_cap)) != cudaSuccess ||
+            (e = ctx->dev_pool.get(b->coef_rows * 128, (void **)&b->d_coef, &b->d_coef_cap)) != cudaSuccess ||
+            (e = ctx->dev_pool.get(b->pix_bytes, (void **)&b->d_pix, &b->d_pix_cap)) != cudaSuccess)
+        {
+            rc = fail_cuda(e, "batch allocation");
+            cudaGetLastError();
+        }
+    }
+    if (rc != B2J_OK) { release_batch_buffers(b); delete b; return rc == B2J_E_CUDA ? B2J_E_NOMEM : rc; }
+
+    // ---- fill the pinned blob
+    memcpy(b->h_blob + b->off_imgs, b->imgs.data(), sizeof(ImgDev) * (size_t)n);
+    memcpy(b->h_blob + b->off_chunk_img, chunk_img.data(), sizeof(uint32_t) * chunk_img.size());
+    memcpy(b->h_blob + b->off_ctas, ctas.data(), sizeof(HuffCtaDev) * ctas.size());
+    memcpy(b->h_blob + b->off_tiles, tiles.data(), sizeof(TileDev) * tiles.size());
+    memcpy(b->h_blob + b->off_luts, luts.data(), sizeof(uint16_t) * luts.size());
+    memcpy(b->h_blob + b->off_qtabs, qtabs.data(), sizeof(uint16_t) * qtabs.size());
+    for (int i = 0; i < n; i++)
+    {
+        const ImgDev &im = b->imgs[(size_t)i];
+        uint8_t *dst = b->h_blob + b->off_raw + im.raw_off;
+        memcpy(dst, files[i] + descs[i].scan_offset, im.raw_len);
+        memset(dst + im.raw_len, 0, align_up((size_t)im.raw_len + 32, 16) - im.raw_len);
+    }
+
+    rc = make_tensor_map(ctx, b);
+    if (rc != B2J_OK) { release_batch_buffers(b); delete b; return rc; }
+
+    DecodeArgs &a = b->args;
+    a.raw = b->d_blob + b->off_raw;
+    a.imgs = reinterpret_cast<const ImgDev *>(b->d_blob + b->off_imgs);
+    a.chunk_img = reinterpret_cast<const uint32_t *>(b->d_blob + b->off_chunk_img);
+    a.huff_ctas = reinterpret_cast<const HuffCtaDev *>(b->d_blob + b->off_ctas);
+    a.tiles = reinterpret_cast<const TileDev *>(b->d_blob + b->off_tiles);
+    a.luts = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_luts);
+    a.qtabs = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_qtabs);
+    a.tmap = &b->tmap;
+    a.clean = b->d_scratch + b->off_clean;
+    a.chunk_cnt = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_cnt);
+    a.chunk_term = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_term);
+    a.chunk_base_keep = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bk);
+    a.chunk_base_mark = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bm);
+    a.clean_len = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_clean_len);
+    a.seg_start = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_seg_start);
+    a.status = reinterpret_cast<int32_t *>(b->d_scratch + b->off_status);
+    a.coef = b->d_coef;
+    a.pixels = b->d_pix;
+    a.n_images = (uint32_t)n;
+    a.n_chunks = (uint32_t)chunk_img.size();
+    a.n_huff_ctas = (uint32_t)ctas.size();
+    a.n_tiles = (uint32_t)tiles.size();
+    a.max_lut_len = max_lut_len;
+    a.use_tma = ctx->use_tma;
+
+    b2j_batch_info &inf = b->info;
+    memset(&inf, 0, sizeof(inf));
+    inf.n_images = n;
+    inf.kernel_launches = 5;
+    inf.total_pixels = pixels;
+    inf.total_blocks = (int64_t)blk_total;
+    inf.scan_bytes = scan_bytes;
+    inf.coef_plane_bytes = 128 * (int64_t)blk_total;
+    inf.pixel_bytes = 4 * pixels;
+    inf.algorithmic_bytes = inf.scan_bytes + 2 * inf.coef_plane_bytes + inf.pixel_bytes;
+    inf.device_bytes = (int64_t)(b->d_blob_cap + b->d_scratch_cap + b->d_coef_cap + b->d_pix_cap);
+    inf.h2d_bytes = (int64_t)b->blob_bytes;
+    *out = b;
+    return B2J_OK;
+}
+
+extern "C" void b2j_batch_destroy(b2j_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    release_batch_buffers(b);
+    delete b;
+}
+
+extern "C" int b2j_batch_get_info(const b2j_batch *b, b2j_batch_info *info)
+{
+    if (!b || !info) return B2J_E_ARG;
+    *info = b->info;
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_upload(b2j_batch *b, void *stream)
+{
+    if (!b) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    CU_TRY(cudaMemcpyAsync(b->d_blob, b->h_blob, b->blob_bytes, cudaMemcpyHostToDevice, s));
+    if (!b->uploaded)
+    {
+        // padding rows of the plane and the tail of the clean stream are read (never used); define them once
+        CU_TRY(cudaMemsetAsync(b->d_coef + (b->coef_rows - kTileBlocks) * 64, 0, (size_t)kTileBlocks * 128, s));
+        CU_TRY(cudaMemsetAsync(b->d_scratch + b->off_clean, 0, b->off_chunk_cnt - b->off_clean, s));
+        b->uploaded = true;
+    }
+    return B2J_OK;
+}
+
+static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* 4 or NULL */)
+{
+    if (!b->uploaded) { t_last_error = "b2j_batch_decode before b2j_batch_upload"; return B2J_E_ARG; }
+    const DecodeArgs &a = b->args;
+    if (ev) CU_TRY(cudaEventRecord(ev[0], s));
+    CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
+    CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
+    launch_prepass(a, s);
+    if (ev) CU_TRY(cudaEventRecord(ev[1], s));
+    launch_huffman(a, s);
+    if (ev) CU_TRY(cudaEventRecord(ev[2], s));
+    launch_idct(a, s);
+    if (ev) CU_TRY(cudaEventRecord(ev[3], s));
+    CU_TRY(cudaGetLastError());
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_decode(b2j_batch *b, void *stream)
+{
+    if (!b) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    return enqueue_decode(b, pick_stream(b, stream), nullptr);
+}
+
+extern "C" int b2j_batch_decode_timed(b2j_batch *b, void *stream, b2j_stage_times *times)
+{
+    if (!b || !times) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; i++) CU_TRY(cudaEventCreate(&ev[i]));
+    int rc = enqueue_decode(b, s, ev);
+    if (rc == B2J_OK)
+    {
+        cudaError_t e = cudaEventSynchronize(ev[3]);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaEventSynchronize");
+        else
+        {
+            cudaEventElapsedTime(&times->prepass_ms, ev[0], ev[1]);
+            cudaEventElapsedTime(&times->huffman_ms, ev[1], ev[2]);
+            cudaEventElapsedTime(&times->idct_ms, ev[2], ev[3]);
+            cudaEventElapsedTime(&times->total_ms, ev[0], ev[3]);
+        }
+    }
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+extern "C" int b2j_batch_sync(b2j_batch *b, void *stream)
+{
+    if (!b) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    CU_TRY(cudaStreamSynchronize(pick_stream(b, stream)));
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_status(b2j_batch *b, void *stream, int32_t *status)
+{
+    if (!b || !status) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    CU_TRY(cudaMemcpyAsync(status, b->args.status, 4 * (size_t)b->n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_pixels_device(const b2j_batch *b, int image, void **dptr, size_t *nbytes)
+{
+    if (!b || image < 0 || image >= b->n || !dptr) return B2J_E_ARG;
+    *dptr = b->d_pix + b->imgs[(size_t)image].pix_off;
+    if (nbytes) *nbytes = (size_t)b->imgs[(size_t)image].width * b->imgs[(size_t)image].height * 4;
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_coefs_device(const b2j_batch *b, int image, void **dptr, size_t *nbytes)
+{
+    if (!b || image < 0 || image >= b->n || !dptr) return B2J_E_ARG;
+    *dptr = b->d_coef + (size_t)b->imgs[(size_t)image].blk_first * 64;
+    if (nbytes) *nbytes = (size_t)b->imgs[(size_t)image].blk_count * 128;
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_read_pixels(b2j_batch *b, void *stream, int image, uint8_t *dst)
+{
+    if (!b || image < 0 || image >= b->n || !dst) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    const ImgDev &im = b->imgs[(size_t)image];
+    CU_TRY(cudaMemcpyAsync(dst, b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_read_all_pixels(b2j_batch *b, void *stream, uint8_t *const *dsts)
+{
+    if (!b || !dsts) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    for (int i = 0; i < b->n; i++)
+    {
+        const ImgDev &im = b->imgs[(size_t)i];
+        if (!dsts[i]) continue;
+        CU_TRY(cudaMemcpyAsync(dsts[i], b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_read_coefs(b2j_batch *b, void *stream, int image, int32_t *dst)
+{
+    if (!b || image < 0 || image >= b->n || !dst) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    const ImgDev &im = b->imgs[(size_t)image];
+    const size_t bytes = (size_t)im.blk_count * 256;
+    if (b->d_expand_cap < bytes)
+    {
+        std::lock_guard<std::mutex> lk(b->ctx->mu);
+        b->ctx->dev_pool.put(b->d_expand, b->d_expand_cap);
+        b->d_expand = nullptr; b->d_expand_cap = 0;
+        cudaError_t e = b->ctx->dev_pool.get(bytes, (void **)&b->d_expand, &b->d_expand_cap);
+        if (e != cudaSuccess) return fail_cuda(e, "coefficient tap allocation");
+    }
+    launch_expand(b->d_coef + (size_t)im.blk_first * 64, b->args.qtabs + (size_t)image * 192, im.blk_count, im.tot_blks, im.ny_blks,
+                  b->d_expand, s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(dst, b->d_expand, bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, int gate,
+                               uint8_t *const *out_bgra, int32_t *status)
+{
+    if (!ctx || n <= 0 || !files || !lens || !out_bgra || !status) return B2J_E_ARG;
+    std::vector<b2j_image_desc> descs;
+    std::vector<const uint8_t *> f;
+    std::vector<size_t> l;
+    std::vector<uint8_t *> o;
+    std::vector<int> idx;
+    descs.reserve((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        b2j_image_desc d;
+        const int rc = b2j_parse_header(files[i], lens[i], gate, &d);
+        status[i] = rc;
+        if (rc != B2J_OK) continue;
+        descs.push_back(d); f.push_back(files[i]); l.push_back(lens[i]); o.push_back(out_bgra[i]); idx.push_back(i);
+    }
+    if (descs.empty()) return B2J_OK;
+    b2j_batch *b = nullptr;
+    int rc = b2j_batch_create(ctx, (int)descs.size(), descs.data(), f.data(), l.data(), &b);
+    if (rc != B2J_OK) return rc;
+    std::vector<int32_t> st(descs.size());
+    if ((rc = b2j_batch_upload(b, nullptr)) == B2J_OK && (rc = b2j_batch_decode(b, nullptr)) == B2J_OK &&
+        (rc = b2j_batch_read_all_pixels(b, nullptr, o.data())) == B2J_OK && (rc = b2j_batch_status(b, nullptr, st.data())) == B2J_OK)
+    {
+        for (size_t k = 0; k < idx.size(); k++) status[idx[k]] = st[k];
+    }
+    b2j_batch_destroy(b);
+    return rc;
+}
