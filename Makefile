@@ -12,7 +12,7 @@ LIB := $(LIBDIR)/libb2j.so
 OBJS := $(OBJDIR)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/host_parse.o $(OBJDIR)/huff_lut.o
 HDRS := $(wildcard $(CSRC)/*.h) include/b2j.h
 
-all: $(LIB) mathcheck oracle
+all: $(LIB) $(BINDIR)/b2jdec mathcheck oracle
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -25,6 +25,12 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDRS)
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+# stand-alone CLI with the reference's argv contract, on the decoder.h-compatible shim
+$(BINDIR)/b2jdec: $(CSRC)/refshim/b2jdec_main.cpp $(CSRC)/refshim/decoder_b2j.cpp $(CSRC)/refshim/refabi.h $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude $(CSRC)/refshim/b2jdec_main.cpp $(CSRC)/refshim/decoder_b2j.cpp \
+	    -L$(LIBDIR) -lb2j -Wl,-rpath,'$$ORIGIN/../lib' -o $@
 
 # host-side unit-check helper: the device arithmetic header + the LUT builder compiled with g++
 mathcheck: tests/native/libb2jcheck.so

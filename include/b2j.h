@@ -22,6 +22,8 @@
  *   b2j_batch_decode        decoder.h:6-7       decode_huffman_data() + decode_mcu_data()
  *                                               (decoder.cpp:262-365, 397-523) and clidct_run()
  *                                               (idct.h:14, oclDCT8x8.cpp:275-299)
+ *   b2j_batch_decode_timed, b2j_batch_decode_steps
+ *                           parser.cpp:373-397  the clock() stage timers of load_jpg(), as CUDA events
  *   b2j_batch_sync          idct.h:17           clidct_wait_for_completion()
  *   b2j_batch_read_pixels   idct.h:16           clidct_retrieve_image_from_device() (tight pitch W*4)
  *   b2j_batch_read_coefs    idct.h:15           clidct_retrieve_data_from_device(): int32[blk][64],
@@ -155,6 +157,10 @@ int b2j_batch_upload(b2j_batch *batch, void *stream);   /* H2D: scan bytes + tab
 int b2j_batch_decode(b2j_batch *batch, void *stream);   /* the hot path, device resident   */
 /* Same as b2j_batch_decode() with CUDA events between the stages; synchronises. */
 int b2j_batch_decode_timed(b2j_batch *batch, void *stream, b2j_stage_times *times);
+/* `steps` decodes back to back on one stream with CUDA events recorded (not waited for) between
+ * the stages of every step; synchronises once at the end. per_step: `steps` entries or NULL.
+ * total_ms: first event of the first step to last event of the last step. */
+int b2j_batch_decode_steps(b2j_batch *batch, void *stream, int steps, b2j_stage_times *per_step, float *total_ms);
 int b2j_batch_sync(b2j_batch *batch, void *stream);
 
 /* Per-image status words (B2J_ST_* bits). Synchronises the stream. */

@@ -16,7 +16,7 @@ B2J_E_NODEVICE = -7
 EXPORTED_SYMBOLS = [
     "b2j_abi_version", "b2j_strerror", "b2j_last_error", "b2j_parse_header", "b2j_device_count",
     "b2j_create", "b2j_destroy", "b2j_batch_create", "b2j_batch_destroy", "b2j_batch_get_info",
-    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_sync", "b2j_batch_status",
+    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status",
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
     "b2j_batch_read_coefs", "b2j_decode_host",
 ]
@@ -96,6 +96,7 @@ def load_library():
     L.b2j_batch_upload.argtypes = [vp, vp]
     L.b2j_batch_decode.argtypes = [vp, vp]
     L.b2j_batch_decode_timed.argtypes = [vp, vp, ctypes.POINTER(StageTimes)]
+    L.b2j_batch_decode_steps.argtypes = [vp, vp, ci, ctypes.POINTER(StageTimes), ctypes.POINTER(ctypes.c_float)]
     L.b2j_batch_sync.argtypes = [vp, vp]
     L.b2j_batch_status.argtypes = [vp, vp, vp]
     L.b2j_batch_pixels_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
@@ -207,6 +208,13 @@ class Batch:
         t = StageTimes()
         _check(self.lib.b2j_batch_decode_timed(self._h, stream, ctypes.byref(t)), "b2j_batch_decode_timed")
         return t
+
+    def decode_steps(self, steps, stream=None):
+        """`steps` decodes back to back; returns (per-step StageTimes array, total ms)."""
+        per = (StageTimes * steps)()
+        total = ctypes.c_float()
+        _check(self.lib.b2j_batch_decode_steps(self._h, stream, steps, per, ctypes.byref(total)), "b2j_batch_decode_steps")
+        return per, total.value
 
     def sync(self, stream=None):
         _check(self.lib.b2j_batch_sync(self._h, stream), "b2j_batch_sync")

@@ -539,6 +539,36 @@ extern "C" int b2j_batch_decode_timed(b2j_batch *b, void *stream, b2j_stage_time
     return rc;
 }
 
+extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j_stage_times *per_step, float *total_ms)
+{
+    if (!b || steps <= 0) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    std::vector<cudaEvent_t> ev((size_t)steps * 4);
+    for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
+    int rc = B2J_OK;
+    for (int k = 0; k < steps && rc == B2J_OK; k++) rc = enqueue_decode(b, s, &ev[(size_t)k * 4]);
+    if (rc == B2J_OK)
+    {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamSynchronize");
+    }
+    if (rc == B2J_OK)
+    {
+        for (int k = 0; k < steps && per_step; k++)
+        {
+            cudaEvent_t *v = &ev[(size_t)k * 4];
+            cudaEventElapsedTime(&per_step[k].prepass_ms, v[0], v[1]);
+            cudaEventElapsedTime(&per_step[k].huffman_ms, v[1], v[2]);
+            cudaEventElapsedTime(&per_step[k].idct_ms, v[2], v[3]);
+            cudaEventElapsedTime(&per_step[k].total_ms, v[0], v[3]);
+        }
+        if (total_ms) cudaEventElapsedTime(total_ms, ev[0], ev[(size_t)steps * 4 - 1]);
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 extern "C" int b2j_batch_sync(b2j_batch *b, void *stream)
 {
     if (!b) return B2J_E_ARG;

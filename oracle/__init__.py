@@ -70,6 +70,11 @@ class Oracle:
         L.orc_sizeof_image.restype = ctypes.c_size_t
         assert L.orc_sizeof_image() == ctypes.sizeof(OrcImage)
 
+    def set_strict(self, strict):
+        """strict=True (default): reproduce the reference's lost-RSTn-at-chunk-end defect
+        (decoder.cpp:118-131); strict=False: the intended behaviour (what the GPU path implements)."""
+        self.lib.orc_set_strict(1 if strict else 0)
+
     def zigzag(self):
         return np.array(list(self.lib.orc_zigzag().contents), dtype=np.int32)
 
@@ -138,7 +143,14 @@ class Reference:
 
     def workdir(self):
         if self._tmp is None:
-            base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+            # the reference writes an uncompressed BMP per image: prefer tmpfs when it has room
+            base = None
+            try:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize > (2 << 30):
+                    base = "/dev/shm"
+            except OSError:
+                pass
             self._tmp = tempfile.TemporaryDirectory(prefix="jpegref_", dir=base)
         return self._tmp.name
 

@@ -20,3 +20,16 @@ g++ -std=c++11 -O2 -fPIC -shared -DNDEBUG -DUSE_CPU_ONLY -w \
     "$src/bitstream.cpp" "$src/huffman.cpp" "$src/cpuIDCT8x8.cpp" "$src/decoder.cpp" "$src/parser.cpp" \
     -o "$here/_ref/libjpegref.so"
 echo "built $here/_ref/libjpegref.so"
+
+# Drop-in proof: the reference's OWN main.cpp + parser.cpp (+ the bit reader / trie units its self
+# tests use), unmodified, linked against this repo's decoder shim instead of decoder.cpp,
+# cpuIDCT8x8.cpp and oclDCT8x8.cpp. Needs ocljpegdecoder_b200/lib/libb2j.so (built by `make`).
+root="$(cd "$here/.." && pwd)"
+if [ -f "$root/ocljpegdecoder_b200/lib/libb2j.so" ]; then
+    g++ -std=c++11 -O2 -DNDEBUG -w -DB2J_USE_REFERENCE_HEADERS -I"$src" \
+        "$src/main.cpp" "$src/parser.cpp" "$src/bitstream.cpp" "$src/huffman.cpp" \
+        "$root/ocljpegdecoder_b200/csrc/refshim/decoder_b2j.cpp" \
+        -L"$root/ocljpegdecoder_b200/lib" -lb2j -Wl,-rpath,'$ORIGIN/../../ocljpegdecoder_b200/lib' \
+        -o "$here/_ref/ocljpegdec_b2j"
+    echo "built $here/_ref/ocljpegdec_b2j (reference main+parser on the B200 decoder shim)"
+fi

@@ -305,25 +305,52 @@ int orc_parse(const uint8_t *file, size_t len, int gate, orc_image *img)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Entropy-coded segment -> clean byte stream: read_more_data<>(), decoder.cpp:94-159.         */
+/* Entropy-coded segment -> clean byte stream: read_more_data<2048>(), decoder.cpp:94-159.    */
 /*   FF 00 -> FF ; FF D0..D7 -> Dn (the FF is dropped, the Dn byte stays in the stream) ;      */
 /*   FF FF -> first FF dropped, second re-examined ; FF D9 -> end ; FF xx (other) -> end.      */
-/* (The reference processes 2 KiB fread chunks and, on "other", also loses the bytes of the    */
-/* current chunk that precede the marker -- a chunk-phase artefact of an already failing       */
-/* stream that is not restated.)                                                               */
+/*                                                                                            */
+/* The reference works on 2 KiB fread chunks and that shows in one case (decoder.cpp:118-131): */
+/* when an FF is the LAST byte of a chunk, the sentinel makes it take the "FF FF" branch,      */
+/* which reads one more byte and re-examines; if that byte is D0..D7 the RSTn branch then      */
+/* appends nothing and the loop ends -- the Dn byte is lost and decode_huffman_data() later    */
+/* stops with "expected RSTn". With g_strict (default) this restatement follows the chunks     */
+/* and reproduces that loss, so that it predicts exactly which files the reference fails on    */
+/* (about 1 in 2048 restart markers); with orc_set_strict(0) it implements the intended        */
+/* behaviour, which is what the GPU path is compared with on such files.                       */
+/* (On "FF xx (other)" the reference also drops the bytes of the current chunk that precede    */
+/* the marker -- an artefact of an already failing stream that is not restated.)               */
+static int g_strict = 1;
+void orc_set_strict(int strict) { g_strict = strict; }
+int orc_get_strict(void) { return g_strict; }
+
 static size_t orc_unstuff(const uint8_t *src, size_t n, uint8_t *dst)
 {
     size_t i = 0, o = 0;
+    size_t chunk_end = n < 2048 ? n : 2048;   /* one past the last byte of the current fread chunk */
     while (i < n)
     {
         const uint8_t b = src[i];
+        int at_chunk_end;
+        if (i >= chunk_end) chunk_end = (n - i < 2048) ? n : i + 2048;
         if (b != 0xFF) { dst[o++] = b; i++; continue; }
-        if (i + 1 >= n) break; /* the reference's sentinel/extra fread finds nothing: stop      */
+        if (i + 1 >= n) break; /* the reference's extra fread finds nothing: stop */
+        at_chunk_end = g_strict && (i + 1 == chunk_end);
+        if (at_chunk_end) chunk_end++;         /* the extra 1-byte fread shifts every later chunk   */
         {
             const uint8_t m = src[i + 1];
             if (m == 0x00) { dst[o++] = 0xFF; i += 2; }
-            else if (m >= 0xD0 && m <= 0xD7) { dst[o++] = m; i += 2; }
-            else if (m == 0xFF) { i += 1; }
+            else if (m >= 0xD0 && m <= 0xD7)
+            {
+                if (!at_chunk_end) dst[o++] = m; /* else: the Dn byte is lost (see above) */
+                i += 2;
+            }
+            else if (m == 0xFF)
+            {
+                /* fill byte: drop this FF and re-examine the next one. At a chunk end the reference */
+                /* keeps pulling single bytes, i.e. the next FF is again "last byte of the chunk".  */
+                i += 1;
+                if (at_chunk_end) chunk_end = i + 1;
+            }
             else break; /* EOI or any other marker */
         }
     }

@@ -1,0 +1,51 @@
+"""Prints the metrics of interest from an `ncu --page raw --csv` dump (profiling helper)."""
+import csv
+import sys
+
+WANT = [
+    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+    'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'smsp__issue_active.avg.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+    'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+    'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
+    'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+    'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+    'smsp__thread_inst_executed_per_inst_executed.ratio',
+    'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+    'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+    'lts__t_sectors_op_write.sum', 'lts__t_sectors_op_read.sum', 'lts__t_bytes.sum',
+    'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_drain_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
+]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+only = sys.argv[2] if len(sys.argv) > 2 else None
+seen = set()
+for r in rows[2:]:
+    name = r[idx['Kernel Name']]
+    if only and only not in name:
+        continue
+    if name in seen:
+        continue
+    seen.add(name)
+    print('=====', name[:60])
+    for w in WANT:
+        if w in idx:
+            print('  %-82s %s %s' % (w, r[idx[w]], units[idx[w]]))

@@ -14,7 +14,8 @@ SUBSAMPLING = {"444": 0, "422": 1, "420": 2}
 
 def synth_pixels(width, height, seed):
     rng = np.random.RandomState(seed)
-    y, x = np.mgrid[0:height, 0:width].astype(np.float32)
+    x = np.arange(width, dtype=np.float32)
+    y = np.arange(height, dtype=np.float32)
     img = np.empty((height, width, 3), dtype=np.float32)
     for c in range(3):
         acc = np.full((height, width), 128.0, dtype=np.float32)
@@ -22,7 +23,8 @@ def synth_pixels(width, height, seed):
             fx, fy = rng.uniform(0.002, 0.08, size=2)
             p1, p2 = rng.uniform(0, 2 * np.pi, size=2)
             amp = rng.uniform(10, 40)
-            acc += amp * np.sin(fx * x + p1) * np.cos(fy * y + p2)
+            # amp*sin(fx*x+p1)*cos(fy*y+p2) over the grid == outer product of two 1-D waves
+            acc += np.outer(np.cos(fy * y + p2).astype(np.float32), (amp * np.sin(fx * x + p1)).astype(np.float32))
         acc += rng.normal(0, 6, size=(height, width)).astype(np.float32)
         img[:, :, c] = acc
     return np.clip(img, 0, 255).astype(np.uint8)
@@ -55,3 +57,22 @@ CONFIGS = {
 def config_jpeg(cfg, index, seed0=1234):
     c = CONFIGS[cfg]
     return synth_jpeg(c["width"], c["height"], seed0 + index, c["quality"], c["subsampling"], c["restart_mcus"])
+
+
+def _config_job(args):
+    cfg, index, seed0 = args
+    return config_jpeg(cfg, index, seed0)
+
+
+def config_batch(cfg, count, first=0, seed0=1234, workers=None):
+    """`count` distinct JPEGs of BASELINE config `cfg`, deterministic per index. Generated on a
+    thread pool (numpy and Pillow's encoder release the GIL), so it is safe to call from a process
+    that already holds a CUDA context -- no fork."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    workers = workers or min(os.cpu_count() or 1, 32)
+    jobs = [(cfg, first + i, seed0) for i in range(count)]
+    if workers <= 1 or count < 4:
+        return [_config_job(j) for j in jobs]
+    with ThreadPoolExecutor(workers) as pool:
+        return list(pool.map(_config_job, jobs))

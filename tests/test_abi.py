@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library loads, exports every symbol include/b2j.h declares, parses headers like
+the oracle does, and refuses to run without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import synth
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ocljpegdecoder_b200 as b2j
+    with open(os.path.join(ROOT, "include", "b2j.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(b2j_[a-z_0-9]+)\s*\(", src)))
+    assert declared, "no declarations found"
+    L = ctypes.CDLL(b2j.library_path())
+    for name in declared:
+        assert hasattr(L, name), "missing export " + name
+    assert sorted(declared) == sorted(b2j.EXPORTED_SYMBOLS)
+    assert L.b2j_abi_version() == 1
+
+
+def test_struct_sizes_match_header(built):
+    import subprocess
+    import tempfile
+    import ocljpegdecoder_b200 as b2j
+    code = '#include "b2j.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu", sizeof(b2j_image_desc), sizeof(b2j_batch_info), sizeof(b2j_stage_times));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        with open(c, "w") as f:
+            f.write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
+    assert [int(x) for x in out] == [ctypes.sizeof(b2j.ImageDesc), ctypes.sizeof(b2j.BatchInfo), ctypes.sizeof(b2j.StageTimes)]
+
+
+def test_parse_header_agrees_with_oracle(built, oracle, fixture_jpeg):
+    import ocljpegdecoder_b200 as b2j
+    files = [fixture_jpeg]
+    for i, (w, h, ss, q, ri, opt) in enumerate([(64, 48, "444", 75, 0, False), (67, 45, "420", 90, 7, True), (130, 70, "422", 85, 2, False)]):
+        files.append(synth.synth_jpeg(w, h, 40 + i, q, ss, ri, opt))
+    for data in files:
+        for gate in (0, 1):
+            rc_o, img = oracle.parse(data, gate)
+            rc, d = b2j.parse_header(data, gate)
+            assert (rc == 0) == (rc_o == 0)
+            if rc != 0:
+                continue
+            assert (d.width, d.height, d.restart_interval) == (img.width, img.height, img.restart_interval)
+            assert (d.mcu_width, d.mcu_height, d.mcu_count_w, d.mcu_count_h, d.mcu_count) == (
+                img.mcu_width, img.mcu_height, img.mcu_count_w, img.mcu_count_h, img.mcu_count)
+            assert list(d.blks_per_mcu) == list(img.blks_per_mcu) and d.blk_count == img.blk_count
+            assert d.scan_offset == img.scan_offset and d.scan_offset + d.scan_size == len(data)
+            for c in range(3):
+                assert d.sampling[c] == img.sampling[c] and d.quant_id[c] == img.quant_id[c] and d.huff_id[c] == img.huff_id[c]
+                assert list(d.quant[d.quant_id[c]]) == list(img.quant[img.quant_id[c]])
+
+
+def test_parse_header_rejects_like_reference(built, oracle, fixture_jpeg):
+    import ocljpegdecoder_b200 as b2j
+    bad = [b"", b"\xff\xd8", fixture_jpeg[:200], b"\x00" + fixture_jpeg[1:], fixture_jpeg.replace(b"\xff\xc0", b"\xff\xc2", 1)]
+    # a COM segment before the tables: load_jpg() stops at unknown markers (parser.cpp:410-412)
+    bad.append(fixture_jpeg[:2] + b"\xff\xfe\x00\x04ab" + fixture_jpeg[2:])
+    for data in bad:
+        rc_o, _ = oracle.parse(data, 1)
+        rc, _ = b2j.parse_header(data, 1)
+        assert rc != 0 and rc_o != 0
+
+
+def test_no_device_no_fallback(built):
+    import ocljpegdecoder_b200 as b2j
+    L = b2j.load_library()
+    if L.b2j_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(b2j.B2JError) as ei:
+        b2j.Decoder(0)
+    assert ei.value.code == -7   # B2J_E_NODEVICE: the product path fails loudly without the device

@@ -1,0 +1,265 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the oracle, the golden vectors and
+the reference build where it travelled. Bar: coefficients bit-exact; pixels within +-1 per channel
+of the cpuIDCT8x8 path (north_star) -- the integer colour path is designed to be exact, so the
+tests assert max |d| <= 1 AND report/assert the mismatch fraction (expected 0)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jpegcraft
+import synth
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, "golden.json")) as f:
+    GOLD = json.load(f)
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name + ".jpg"), "rb") as f:
+        return f.read()
+
+
+def _decode(decoder, files):
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    st = batch.status()
+    coefs = [batch.coefs(i) for i in range(len(files))]
+    pix = [batch.pixels(i) for i in range(len(files))]
+    batch.close()
+    return st, coefs, pix
+
+
+def _check_pixels(got, want):
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    frac = float((d > 0).mean())
+    assert d.max() <= 1, "pixel difference above +-1 (max %d)" % d.max()
+    assert frac == 0.0, "pixel mismatch fraction %.3e (within +-1 but the integer path should be exact)" % frac
+
+
+def test_golden_vectors(decoder):
+    names = sorted(GOLD)
+    files = [_load(n) for n in names]
+    st, coefs, pix = _decode(decoder, files)
+    assert not st.any(), st
+    for n, c, p in zip(names, coefs, pix):
+        g = GOLD[n]
+        assert c.shape == (g["blk_count"], 64) and p.shape == (g["height"], g["width"], 4)
+        assert hashlib.sha256(c.tobytes()).hexdigest() == g["coef_sha256"], n
+        assert hashlib.sha256(p.tobytes()).hexdigest() == g["pixel_sha256"], n
+
+
+def test_reference_fixture_hashes(decoder, fixture_jpeg):
+    st, coefs, pix = _decode(decoder, [fixture_jpeg])
+    assert st[0] == 0
+    assert hashlib.sha256(coefs[0].tobytes()).hexdigest() == "c25806f5238c8ec7c2a4846cf6b67c5b567fd268599591392baf77e91023924e"
+    assert hashlib.sha256(pix[0].tobytes()).hexdigest() == "efb49cf99f2f6c583c546d6ef24c5d26ae339955c8bbe467341933aafa9b16e5"
+
+
+SPECS = [(64, 48, "444", 75, 0, False), (67, 45, "420", 90, 0, False), (67, 45, "420", 90, 1, False),
+         (200, 120, "420", 50, 3, True), (130, 70, "422", 85, 0, False), (130, 70, "422", 85, 2, True),
+         (640, 480, "420", 90, 16, False), (640, 480, "444", 95, 7, True), (333, 211, "444", 95, 5, False),
+         (500, 375, "420", 75, 0, False), (16, 16, "420", 100, 0, False), (8, 8, "444", 10, 0, False),
+         (1, 1, "420", 90, 0, False), (17, 9, "422", 60, 1, False), (1023, 31, "420", 35, 5, True),
+         (31, 1023, "444", 99, 2, False), (1920, 1080, "420", 90, 16, False), (1280, 720, "422", 85, 40, False)]
+
+
+def test_synthetic_mixed_batch_against_oracle(decoder, oracle):
+    """All layouts, odd sizes, optimised/standard tables, RI dividing and not dividing the MCU row,
+    decoded as ONE batch (one launch per kernel for all of them)."""
+    files = [synth.synth_jpeg(w, h, 300 + i, q, ss, ri, opt) for i, (w, h, ss, q, ri, opt) in enumerate(SPECS)]
+    st, coefs, pix = _decode(decoder, files)
+    assert not st.any(), st
+    oracle.set_strict(False)
+    try:
+        for f, c, p in zip(files, coefs, pix):
+            rc, img, coef, bgra = oracle.decode(f)
+            assert rc == 0
+            assert np.array_equal(c, coef)
+            _check_pixels(p, bgra)
+    finally:
+        oracle.set_strict(True)
+
+
+def test_against_reference_build(decoder, reference):
+    files = [synth.synth_jpeg(w, h, 700 + i, q, ss, ri, opt) for i, (w, h, ss, q, ri, opt) in enumerate(SPECS[:12])]
+    st, coefs, pix = _decode(decoder, files)
+    assert not st.any()
+    n_checked = 0
+    for (w, h, ss, q, ri, opt), f, c, p in zip(SPECS, files, coefs, pix):
+        ok, info, rcoef, rbgra, _ = reference.decode(f, skip_gate=(ss == "422"))
+        if not ok:
+            continue   # the reference's own RSTn-at-chunk-end defect (see test_oracle.py)
+        assert np.array_equal(c, rcoef)
+        _check_pixels(p, rbgra)
+        n_checked += 1
+    assert n_checked >= 8
+
+
+def _crafted(sampling, w, h, ri, fill, seed, stuffed=False):
+    rng = np.random.RandomState(seed)
+    ny = sampling[0] * sampling[1]
+    tot = ny + 2
+    n_mcu = ((w + 8 * sampling[0] - 1) // (8 * sampling[0])) * ((h + 8 * sampling[1] - 1) // (8 * sampling[1]))
+    blocks = np.zeros((n_mcu * tot, 64), np.int64)
+    for b in range(len(blocks)):
+        kind = (b + seed) % 6
+        if kind == 0:
+            blocks[b, 1:] = rng.randint(1, 4, 63) * rng.choice([-1, 1], 63)      # all 63 AC set, no EOB
+        elif kind == 1:
+            blocks[b, 50 + b % 13] = int(rng.randint(1, 30))                     # ZRL chains
+        elif kind == 3:
+            blocks[b, 1:6] = rng.randint(-1023, 1023, 5)                         # maximum baseline magnitudes
+        elif kind == 4:
+            blocks[b, 63] = -1
+        elif kind == 5 and stuffed:
+            blocks[b, 1:40] = -1 if b % 2 else 1                                 # long runs of 1 bits -> FF00 stuffing
+    dc = np.cumsum(rng.randint(-300, 300, len(blocks)))
+    blocks[:, 0] = np.clip(dc, -1000, 1000)
+    blocks[::7, 0] = blocks[1::7, 0][:len(blocks[::7])] if len(blocks) > 8 else 0  # DC difference 0 (category 0)
+    q = [[1 + (i % 7) for i in range(64)], [2 + (i % 5) for i in range(64)]]
+    return jpegcraft.build_jpeg(w, h, sampling, blocks, q, restart_interval=ri, fill_before_rst=fill)
+
+
+def test_crafted_edge_streams(decoder, oracle):
+    files = []
+    for sampling, (w, h) in (((2, 2), (80, 48)), ((1, 1), (40, 24)), ((2, 1), (80, 24)), ((1, 2), (40, 48))):
+        for ri, fill in ((0, 0), (1, 0), (2, 3), (9, 1)):
+            files.append(_crafted(sampling, w, h, ri, fill, seed=len(files), stuffed=True))
+    st, coefs, pix = _decode(decoder, files)
+    assert not st.any(), st
+    oracle.set_strict(False)
+    try:
+        for f, c, p in zip(files, coefs, pix):
+            rc, img, coef, bgra = oracle.decode(f)
+            assert rc == 0
+            assert f.count(b"\xff\x00") > 0
+            assert np.array_equal(c, coef)
+            # crafted blocks drive the IDCT far outside [-256,255]; the reference's clip table only
+            # covers +-512 (cpuIDCT8x8.cpp:13-23, undefined beyond), the oracle and the GPU both clamp
+            _check_pixels(p, bgra)
+    finally:
+        oracle.set_strict(True)
+
+
+def test_many_restart_intervals_wrap_mod8(decoder, oracle):
+    # 2400 intervals in one image: RSTn numbering wraps 300 times; several CTAs per image
+    f = synth.synth_jpeg(1280, 480, 77, 85, "420", 1)
+    st, coefs, pix = _decode(decoder, [f])
+    assert st[0] == 0
+    oracle.set_strict(False)
+    try:
+        rc, _, coef, bgra = oracle.decode(f)
+    finally:
+        oracle.set_strict(True)
+    assert rc == 0 and np.array_equal(coefs[0], coef)
+    _check_pixels(pix[0], bgra)
+
+
+def test_corrupt_streams_are_flagged(decoder, oracle):
+    good = synth.synth_jpeg(320, 240, 5, 90, "420", 4)
+    rc, d = oracle.parse(good)
+    off = d.scan_offset
+    cases = {}
+    # RSTn out of sequence
+    b = bytearray(good)
+    k = good.index(b"\xff\xd1", off)
+    b[k + 1] = 0xD5
+    cases["rst_sequence"] = bytes(b)
+    # a restart marker removed
+    k = good.index(b"\xff\xd2", off)
+    cases["rst_missing"] = good[:k] + good[k + 2:]
+    # truncated in the middle of the scan
+    cases["truncated"] = good[:off + (len(good) - off) // 2]
+    # garbage bits in the middle of an interval
+    b = bytearray(good)
+    mid = off + (len(good) - off) // 3
+    for j in range(24):
+        if b[mid + j] != 0xFF and b[mid + j - 1] != 0xFF:
+            b[mid + j] ^= 0x5A
+    cases["bitflips"] = bytes(b)
+    names = sorted(cases)
+    st, _, _ = _decode(decoder, [cases[n] for n in names] + [good])
+    assert st[-1] == 0
+    for n, s in zip(names, st[:-1]):
+        rc, *_ = oracle.decode(cases[n], want_pixels=False)
+        if rc != 0:
+            assert s != 0, "%s: the reference path fails but the GPU status is clean" % n
+
+
+def test_decode_is_idempotent_and_batch_invariant(decoder):
+    files = [synth.synth_jpeg(w, h, 20 + i, q, ss, ri) for i, (w, h, ss, q, ri, _) in enumerate(SPECS[:8])]
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    a = [batch.pixels(i).copy() for i in range(len(files))]
+    batch.decode_steps(3)
+    b = [batch.pixels(i) for i in range(len(files))]
+    batch.close()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # each image alone == the same image inside the batch
+    for i in (1, 5):
+        st, _, pix = _decode(decoder, [files[i]])
+        assert st[0] == 0 and np.array_equal(pix[0], a[i])
+
+
+def test_decode_host_api(decoder, oracle, fixture_jpeg):
+    files = [fixture_jpeg, synth.synth_jpeg(256, 192, 7, 90, "420", 4), b"not a jpeg", synth.synth_jpeg(96, 64, 9, 80, "444", 0)]
+    outs, st = decoder.decode_host(files)
+    assert st[2] < 0 and st[0] == 0 and st[1] == 0 and st[3] == 0
+    for i in (0, 1, 3):
+        rc, _, _, bgra = oracle.decode(files[i])
+        assert rc == 0
+        _check_pixels(outs[i], bgra)
+
+
+def test_full_size_config2_batch(decoder, oracle):
+    """BASELINE configs[1] at full size: 256 x 1080p 4:2:0 q90 RI=16. Exact comparison on a sample;
+    for the whole batch: clean status, idempotence of the pixel checksum, and the checksum of every
+    image decoded in the big batch equals the checksum of the same image decoded in a small batch."""
+    files = synth.config_batch(1, 256)
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    sums = [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in range(0, 256, 5)]
+    batch.decode_steps(2)
+    sums2 = [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in range(0, 256, 5)]
+    assert sums == sums2
+    oracle.set_strict(False)
+    try:
+        for i in (0, 37, 101, 255):
+            rc, _, coef, bgra = oracle.decode(files[i])
+            assert rc == 0
+            assert np.array_equal(batch.coefs(i), coef)
+            _check_pixels(batch.pixels(i), bgra)
+    finally:
+        oracle.set_strict(True)
+    batch.close()
+    st, _, pix = _decode(decoder, [files[k] for k in (10, 250)])
+    assert not st.any()
+    assert hashlib.sha256(pix[0].tobytes()).hexdigest() == sums[2]
+    assert hashlib.sha256(pix[1].tobytes()).hexdigest() == sums[50]
+
+
+@pytest.mark.parametrize("cfg,count", [(2, 2), (3, 1), (4, 64)])
+def test_other_baseline_configs(decoder, oracle, cfg, count):
+    """configs[2..4] (4K 4:4:4 q95, 8K 4:2:2 q85, 500x375 4:2:0 q75): streams without restart markers."""
+    files = synth.config_batch(cfg, count)
+    st, coefs, pix = _decode(decoder, files)
+    assert not st.any()
+    oracle.set_strict(False)
+    try:
+        for i in sorted(set([0, count - 1])):
+            rc, _, coef, bgra = oracle.decode(files[i])
+            assert rc == 0
+            assert np.array_equal(coefs[i], coef)
+            _check_pixels(pix[i], bgra)
+    finally:
+        oracle.set_strict(True)

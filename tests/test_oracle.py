@@ -1,0 +1,129 @@
+"""CPU: pins the oracle (oracle/oracle.c) against the reference's own fixture hashes, the committed
+golden vectors, and -- where it was built -- the unmodified reference compiled from source."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jpegcraft
+import synth
+from conftest import GOLDEN
+
+with open(os.path.join(GOLDEN, "golden.json")) as f:
+    GOLD = json.load(f)
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name + ".jpg"), "rb") as f:
+        return f.read()
+
+
+def test_fixture_hashes_match_survey(oracle, fixture_jpeg):
+    # hashes of the reference CPU path on its own fixture
+    rc, img, coef, bgra = oracle.decode(fixture_jpeg, gate=0)
+    assert rc == 0
+    assert (img.width, img.height, img.blk_count, img.mcu_count) == (313, 234, 1800, 300)
+    assert hashlib.sha256(coef.tobytes()).hexdigest() == "c25806f5238c8ec7c2a4846cf6b67c5b567fd268599591392baf77e91023924e"
+    assert hashlib.sha256(bgra.tobytes()).hexdigest() == "efb49cf99f2f6c583c546d6ef24c5d26ae339955c8bbe467341933aafa9b16e5"
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_oracle_matches_golden(oracle, name):
+    data = _load(name)
+    g = GOLD[name]
+    assert hashlib.sha256(data).hexdigest() == g["file_sha256"]
+    rc, img, coef, bgra = oracle.decode(data, gate=1 if g["needs_extended_gate"] else 0)
+    assert rc == 0
+    assert (img.width, img.height, img.blk_count) == (g["width"], g["height"], g["blk_count"])
+    assert hashlib.sha256(coef.tobytes()).hexdigest() == g["coef_sha256"]
+    assert hashlib.sha256(bgra.tobytes()).hexdigest() == g["pixel_sha256"]
+
+
+def test_reference_gate_rejects_422(oracle):
+    data = _load("g422_q85")
+    rc, _ = oracle.parse(data, gate=0)
+    assert rc == -2          # decoder.cpp:58-69 admits only 4:2:0 and 4:4:4
+    rc, _ = oracle.parse(data, gate=1)
+    assert rc == 0
+
+
+def test_zigzag_is_standard(oracle):
+    zz = oracle.zigzag()
+    assert sorted(zz.tolist()) == list(range(64))
+    assert zz[:10].tolist() == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24] and zz[63] == 63
+
+
+CASES = [(64, 48, "444", 75, 0, False), (67, 45, "420", 90, 0, False), (67, 45, "420", 90, 1, False),
+         (200, 120, "420", 50, 3, True), (130, 70, "422", 85, 0, False), (130, 70, "422", 85, 2, True),
+         (500, 375, "420", 75, 0, False), (333, 211, "444", 95, 5, True), (16, 16, "420", 100, 0, False),
+         (640, 360, "420", 90, 16, False)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_build(oracle, reference, case):
+    w, h, ss, q, ri, opt = case
+    data = synth.synth_jpeg(w, h, 500 + w + h, q, ss, ri, opt)
+    ok, info, rcoef, rbgra, _ = reference.decode(data, skip_gate=(ss == "422"))
+    rc, img, coef, bgra = oracle.decode(data, gate=1)
+    assert ok == (rc == 0)
+    if ok:
+        assert np.array_equal(coef, rcoef)
+        assert np.array_equal(bgra, rbgra)
+
+
+def test_oracle_reproduces_reference_rst_defect(oracle, reference):
+    """The reference drops an RSTn whose FF is the last byte of one of its 2 KiB reads and then
+    aborts (decoder.cpp:118-131). strict mode predicts exactly those files; non-strict decodes them."""
+    n_fail = 0
+    for i in range(24):
+        data = synth.synth_jpeg(640, 480, 900 + i, 90, "420", 1)   # 1200 restart markers per image
+        ok, _, rcoef, _, _ = reference.decode(data, want_pixels=False)
+        oracle.set_strict(True)
+        rc_s, _, coef_s, _ = oracle.decode(data, want_pixels=False)
+        oracle.set_strict(False)
+        rc_n, _, coef_n, _ = oracle.decode(data, want_pixels=False)
+        oracle.set_strict(True)
+        assert ok == (rc_s == 0)
+        assert rc_n == 0
+        if ok:
+            assert np.array_equal(coef_s, rcoef) and np.array_equal(coef_n, rcoef)
+        else:
+            n_fail += 1
+    assert n_fail > 0   # with 1200 markers per image the defect shows up in this sample
+
+
+def test_crafted_streams_oracle_vs_reference(oracle, reference):
+    rng = np.random.RandomState(5)
+    zz = oracle.zigzag()
+    for sampling, (w, h) in (((2, 2), (48, 32)), ((1, 1), (24, 16)), ((2, 1), (48, 16))):
+        ny = sampling[0] * sampling[1]
+        tot = ny + 2
+        n_mcu = ((w + 8 * sampling[0] - 1) // (8 * sampling[0])) * ((h + 8 * sampling[1] - 1) // (8 * sampling[1]))
+        blocks = np.zeros((n_mcu * tot, 64), np.int64)
+        for b in range(len(blocks)):
+            kind = b % 5
+            if kind == 0:      # full block, no EOB
+                blocks[b, 1:] = rng.randint(1, 4, 63) * rng.choice([-1, 1], 63)
+            elif kind == 1:    # ZRL chains: one coefficient far out
+                blocks[b, 50 + b % 13] = rng.randint(-30, 30) or 7
+            elif kind == 2:    # DC only
+                pass
+            elif kind == 3:    # big magnitudes
+                blocks[b, 1:6] = rng.randint(-1023, 1023, 5)
+            else:              # last coefficient set
+                blocks[b, 63] = -1
+        blocks[:, 0] = np.clip(np.cumsum(rng.randint(-300, 300, len(blocks))), -1000, 1000)
+        q = [[1 + (i % 7) for i in range(64)], [2 + (i % 5) for i in range(64)]]
+        for ri, fill in ((0, 0), (1, 0), (2, 3)):
+            data = jpegcraft.build_jpeg(w, h, sampling, blocks, q, restart_interval=ri, fill_before_rst=fill)
+            rc, img, coef, _ = oracle.decode(data, gate=1, want_pixels=False)
+            ok, _, rcoef, _, _ = reference.decode(data, skip_gate=True, want_pixels=False)
+            assert rc == 0 and ok
+            assert np.array_equal(coef, rcoef)
+            exp = np.zeros_like(coef)
+            for b in range(len(blocks)):
+                qq = np.array(q[0] if b % tot < ny else q[1])
+                exp[b, zz] = blocks[b] * qq
+            assert np.array_equal(coef, exp)
