@@ -22,12 +22,14 @@ constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
 constexpr uint32_t kNoTerm = 0xFFFFu;
 
-// LUT entry (u16):
-//   leaf   : bit15 = 0; bits 0-4 code length (1..16, 0 = no codeword has this prefix);
-//            bits 5-9 value-bit count (AC: size nibble; DC: category); bits 10-13 zero run
-//   escape : bit15 = 1; bits 0-3 extra index bits nb (1..16-kLutBits);
-//            bits 4-14 sub-table offset relative to the end of the primary table
-constexpr uint16_t kLutEscape = 0x8000;
+// LUT entry (u16), laid out so that the decode loop needs no arithmetic on the fields:
+//   leaf    : bits 0-5  = 32 + code length (33..48)      -> bit position advances by field0 - field1
+//             bits 6-11 = 32 - value-bit count (16..32)     (AC: size nibble; DC: category)
+//             bits 12-15 = zero run
+//   escape  : bits 0-5  = extra index bits nb (1..16-kLutBits, i.e. < 32), bits 6-15 = sub-table
+//             offset relative to the end of the primary table
+//   invalid : 0 (no codeword has this prefix)
+constexpr uint32_t kLutSubMax = 1024;    // sub-table entries addressable by an escape
 
 // sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)
 enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3 };
@@ -59,7 +61,14 @@ struct ImgDev
 };
 
 struct HuffCtaDev { uint32_t img; uint32_t seg_first; };   // segment index local to the image
-struct TileDev { uint32_t img; uint32_t mcu_first; };
+// One IDCT/colour tile: up to kTileBlocks consecutive blocks (whole MCUs) of one image.
+struct TileDev
+{
+    uint32_t img;
+    uint32_t mcu_first;   // first MCU of the tile inside the image
+    uint32_t row_first;   // first row of the tile in the coefficient plane (the TMA y coordinate)
+    uint32_t info;        // SamplingMode | n_mcus << 8
+};
 
 // ---------------------------------------------------------------- host helpers ---------
 // Canonical Huffman table -> two-level LUT. Returns false when the table cannot be built

@@ -82,9 +82,10 @@ B2J_HD int32_t iclip(int32_t v) // the iclp table of cpuIDCT8x8.cpp:13-23: [-256
     return v < -256 ? -256 : (v > 255 ? 255 : v);
 }
 
-// One column (cpuIDCT8x8.cpp:82-127), outputs clipped to [-256,255].
-B2J_HD void idct_col(int32_t &b0, int32_t &b1, int32_t &b2, int32_t &b3, int32_t &b4, int32_t &b5,
-                     int32_t &b6, int32_t &b7)
+// One column (cpuIDCT8x8.cpp:82-127) up to and including the final >>14, WITHOUT the iclp clip
+// (the kernel clips two values at a time after packing them to int16 pairs).
+B2J_HD void idct_col_noclip(int32_t &b0, int32_t &b1, int32_t &b2, int32_t &b3, int32_t &b4, int32_t &b5,
+                            int32_t &b6, int32_t &b7)
 {
     int32_t x0 = b0 * 256 + 8192, x1 = b4 * 256, x2 = b6, x3 = b2, x4 = b1, x5 = b7, x6 = b5, x7 = b3, x8;
     x8 = IW7 * (x4 + x5) + 4;
@@ -108,14 +109,23 @@ B2J_HD void idct_col(int32_t &b0, int32_t &b1, int32_t &b2, int32_t &b3, int32_t
     x0 -= x2;
     x2 = (181 * (x4 + x5) + 128) >> 8;
     x4 = (181 * (x4 - x5) + 128) >> 8;
-    b0 = iclip((x7 + x1) >> 14);
-    b1 = iclip((x3 + x2) >> 14);
-    b2 = iclip((x0 + x4) >> 14);
-    b3 = iclip((x8 + x6) >> 14);
-    b4 = iclip((x8 - x6) >> 14);
-    b5 = iclip((x0 - x4) >> 14);
-    b6 = iclip((x3 - x2) >> 14);
-    b7 = iclip((x7 - x1) >> 14);
+    b0 = (x7 + x1) >> 14;
+    b1 = (x3 + x2) >> 14;
+    b2 = (x0 + x4) >> 14;
+    b3 = (x8 + x6) >> 14;
+    b4 = (x8 - x6) >> 14;
+    b5 = (x0 - x4) >> 14;
+    b6 = (x3 - x2) >> 14;
+    b7 = (x7 - x1) >> 14;
+}
+
+// One column with the reference's clip to [-256,255].
+B2J_HD void idct_col(int32_t &b0, int32_t &b1, int32_t &b2, int32_t &b3, int32_t &b4, int32_t &b5,
+                     int32_t &b6, int32_t &b7)
+{
+    idct_col_noclip(b0, b1, b2, b3, b4, b5, b6, b7);
+    b0 = iclip(b0); b1 = iclip(b1); b2 = iclip(b2); b3 = iclip(b3);
+    b4 = iclip(b4); b5 = iclip(b5); b6 = iclip(b6); b7 = iclip(b7);
 }
 
 // Full 8x8 block held as 64 scalars (a thread's registers on the device).

@@ -18,7 +18,7 @@ inline uint16_t leaf_entry(int len, int sym, bool is_dc)
     int size, run;
     if (is_dc) { size = sym; run = 0; if (size > 16) return 0; }   // category > 16: not decodable here
     else { size = sym & 15; run = sym >> 4; }
-    return (uint16_t)(len | (size << 5) | (run << 10));
+    return (uint16_t)((32 + len) | ((32 - size) << 6) | (run << 12));
 }
 } // namespace
 
@@ -64,9 +64,9 @@ bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
         if (!maxlen[p]) continue;
         const int nb = maxlen[p] - K;
         const size_t rel = out.size() - ((size_t)1 << K);
-        if (rel >= 2048) return false;
+        if (rel + ((size_t)1 << nb) > kLutSubMax) return false;
         sub_off[p] = (uint32_t)out.size();
-        out[p] = (uint16_t)(kLutEscape | nb | (rel << 4));
+        out[p] = (uint16_t)(nb | (rel << 6));
         out.resize(out.size() + ((size_t)1 << nb), 0);
         if (out.size() > max_entries) return false;
     }

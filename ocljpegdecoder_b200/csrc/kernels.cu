@@ -50,72 +50,112 @@ cudaError_t init_constants()
 //             kept otherwise.
 // The reference keeps the Dn byte in its stream and consumes it at the interval switch
 // (decoder.cpp:136-141, 296-297); here it is dropped and becomes a segment boundary instead.
-struct ScanFlags { uint32_t keep, mark, term; };   // one bit per byte of the thread's 16
+//
+// The classification runs on 4 bytes at a time in a "flag" domain: bit 7 of every byte of a 32-bit
+// word is the predicate for that byte (byte j of the thread = bits 8(j&3).. of word j>>2).
+struct ScanFlags { uint32_t keep[4], mark[4], term[4]; };
 
-__device__ __forceinline__ ScanFlags classify16(const uint8_t *__restrict__ scan, uint32_t raw_len, uint32_t pos, uint32_t bytes[4])
+constexpr uint32_t kFlagAll = 0x80808080u;
+
+__device__ __forceinline__ uint32_t eq_ff(uint32_t w)   // flag set where the byte is 0xFF
 {
-    ScanFlags f = {0u, 0u, 0u};
-    if (pos >= raw_len) { bytes[0] = bytes[1] = bytes[2] = bytes[3] = 0; return f; }
-    const uint4 v = *reinterpret_cast<const uint4 *>(scan + pos);   // scan base and pos are 16 B aligned
-    bytes[0] = v.x; bytes[1] = v.y; bytes[2] = v.z; bytes[3] = v.w;
-    uint32_t p = pos ? scan[pos - 1] : 0u;
-    const uint32_t after = (pos + 16 < raw_len) ? scan[pos + 16] : 0xD9u;   // running off the end acts like EOI
+    return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & kFlagAll;
+}
+// flags of the first n bytes (n in 0..16) of the thread's 16
+__device__ __forceinline__ void first_n_flags(int n, uint32_t m[4])
+{
 #pragma unroll
-    for (int j = 0; j < 16; j++)
+    for (int i = 0; i < 4; i++)
     {
-        const uint32_t b = (bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        uint32_t n;
-        if (j < 15) n = (bytes[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xFFu; else n = after;
-        const bool inside = pos + j < raw_len;
-        if (pos + j + 1 >= raw_len) n = 0xD9u;
-        const bool n_rst = (n & 0xF8u) == 0xD0u;
-        const bool b_rst = (b & 0xF8u) == 0xD0u;
-        bool keep, mark = false, term = false;
-        if (b == 0xFFu) { keep = (n == 0x00u); term = !(n == 0x00u || n == 0xFFu || n_rst); }
-        else { mark = (p == 0xFFu) && b_rst; keep = !((p == 0xFFu) && (b == 0x00u || b_rst)); }
-        if (inside)
-        {
-            f.keep |= (uint32_t)keep << j;
-            f.mark |= (uint32_t)mark << j;
-            f.term |= (uint32_t)term << j;
-        }
-        p = b;
+        const int r = n - 4 * i;
+        m[i] = r >= 4 ? kFlagAll : (r <= 0 ? 0u : (kFlagAll & ((1u << (8 * r)) - 1u)));
+    }
+}
+// 16 flags -> one word with 16 distinct bits (order scrambled; only used for counting / any-tests)
+__device__ __forceinline__ uint32_t squeeze(const uint32_t f[4]) { return (f[0] >> 7) | (f[1] >> 6) | (f[2] >> 5) | (f[3] >> 4); }
+__device__ __forceinline__ bool flag_at(const uint32_t f[4], int j) { return (f[j >> 2] >> (8 * (j & 3) + 7)) & 1u; }
+
+// The host pads every image's scan with FF D9 D9 ..., so running off the end looks like EOI and no
+// end-of-data special case is needed: the pad FF is a terminator and everything behind it is cut.
+__device__ __forceinline__ ScanFlags classify16(const uint8_t *__restrict__ scan, uint32_t raw_len, uint32_t pos, uint32_t w[4])
+{
+    ScanFlags f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) f.keep[i] = f.mark[i] = f.term[i] = 0u;
+    if (pos > raw_len) { w[0] = w[1] = w[2] = w[3] = 0; return f; }
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(scan + pos));   // scan base and pos are 16 B aligned
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    const uint32_t prev = pos ? (uint32_t)__ldg(scan + pos - 1) : 0u;      // byte before the thread's 16
+    const uint32_t next = (uint32_t)__ldg(scan + pos + 16);                // byte after (pad bytes exist)
+    uint32_t F[6], Z[5], D[5];   // index i+1 = word i; F[0] = predecessor, [5] = successor
+    F[0] = prev == 0xFFu ? 0x80000000u : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        F[i + 1] = eq_ff(w[i]);
+        Z[i] = eq_ff(~w[i]);
+        D[i] = eq_ff((w[i] | 0x07070707u) ^ 0x28282828u);   // (b & 0xF8) == 0xD0
+    }
+    F[5] = next == 0xFFu ? 0x80u : 0u;
+    Z[4] = next == 0x00u ? 0x80u : 0u;
+    D[4] = (next & 0xF8u) == 0xD0u ? 0x80u : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const uint32_t Fi = F[i + 1];
+        const uint32_t Fp = __funnelshift_l(F[i], Fi, 8);          // flag of the previous byte
+        const uint32_t Fn = __funnelshift_r(Fi, F[i + 2], 8);      // flags of the next byte
+        const uint32_t Zn = __funnelshift_r(Z[i], Z[i + 1], 8);
+        const uint32_t Dn = __funnelshift_r(D[i], D[i + 1], 8);
+        f.keep[i] = ((Fi & Zn) | (~Fi & ~(Fp & (Z[i] | D[i])))) & kFlagAll;
+        f.mark[i] = ~Fi & Fp & D[i];
+        f.term[i] = Fi & ~(Zn | Fn | Dn);
     }
     return f;
 }
 
-// Chunk-local position of the first terminator, or 0xFFFF.
-__device__ __forceinline__ uint32_t block_first_term(uint32_t term_bits, uint32_t tid, uint32_t *s_min)
+// Chunk-local position of the first terminator, or kNoTerm.
+__device__ __forceinline__ uint32_t block_first_term(const uint32_t term[4], uint32_t tid, uint32_t *s_min)
 {
     if (tid == 0) *s_min = kNoTerm;
     __syncthreads();
-    if (term_bits) atomicMin(s_min, tid * 16u + (uint32_t)(__ffs(term_bits) - 1));
+    if (term[0] | term[1] | term[2] | term[3])
+    {
+        uint32_t j = 0;
+        if (term[0]) j = (uint32_t)(__ffs(term[0]) - 1) >> 3;
+        else if (term[1]) j = 4u + ((uint32_t)(__ffs(term[1]) - 1) >> 3);
+        else if (term[2]) j = 8u + ((uint32_t)(__ffs(term[2]) - 1) >> 3);
+        else j = 12u + ((uint32_t)(__ffs(term[3]) - 1) >> 3);
+        atomicMin(s_min, tid * 16u + j);
+    }
     __syncthreads();
     return *s_min;
 }
 
-__device__ __forceinline__ uint32_t mask_below(uint32_t tid, uint32_t limit)   // bits of this thread's bytes that lie below `limit`
+// Drops the flags of bytes at or behind the chunk-local terminator position.
+__device__ __forceinline__ void cut_at(uint32_t term_pos, uint32_t tid, uint32_t keep[4], uint32_t mark[4])
 {
-    const uint32_t lo = tid * 16u;
-    if (limit >= lo + 16u) return 0xFFFFu;
-    if (limit <= lo) return 0u;
-    return (1u << (limit - lo)) - 1u;
+    if (term_pos >= tid * 16u + 16u) return;
+    uint32_t m[4];
+    first_n_flags(term_pos > tid * 16u ? (int)(term_pos - tid * 16u) : 0, m);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { keep[i] &= m[i]; mark[i] &= m[i]; }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_count(const uint8_t *__restrict__ raw, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ chunk_img,
-             uint32_t *__restrict__ chunk_cnt, uint32_t *__restrict__ chunk_term)
+             uint32_t *__restrict__ chunk_cnt, uint32_t *__restrict__ chunk_term, uint32_t chunk0)
 {
     __shared__ uint32_t s_min;
     __shared__ uint32_t s_warp[kScanThreads / 32];
-    const uint32_t c = blockIdx.x, tid = threadIdx.x;
+    const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x;
     const ImgDev &im = imgs[chunk_img[c]];
     const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * 16u;
-    uint32_t bytes[4];
-    const ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, bytes);
+    uint32_t w[4];
+    ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, w);
     const uint32_t term = block_first_term(f.term, tid, &s_min);
-    const uint32_t live = mask_below(tid, term);
-    uint32_t packed = __popc(f.keep & live) | (__popc(f.mark & live) << 16);
+    cut_at(term, tid, f.keep, f.mark);
+    uint32_t packed = __popc(squeeze(f.keep)) | (__popc(squeeze(f.mark)) << 16);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
     if ((tid & 31) == 0) s_warp[tid >> 5] = packed;
@@ -124,7 +164,7 @@ k_scan_count(const uint8_t *__restrict__ raw, const ImgDev *__restrict__ imgs, c
     {
         uint32_t tot = 0;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; w++) tot += s_warp[w];
+        for (int w8 = 0; w8 < kScanThreads / 32; w8++) tot += s_warp[w8];
         chunk_cnt[c] = tot;
         chunk_term[c] = term;
     }
@@ -132,14 +172,14 @@ k_scan_count(const uint8_t *__restrict__ raw, const ImgDev *__restrict__ imgs, c
 
 // One warp per image: exclusive scan of the chunk counts, truncated at the first terminator.
 __global__ void __launch_bounds__(128)
-k_scan_chunks(const ImgDev *__restrict__ imgs, int n_images, const uint32_t *__restrict__ chunk_cnt,
+k_scan_chunks(const ImgDev *__restrict__ imgs, int img0, int img1, const uint32_t *__restrict__ chunk_cnt,
               const uint32_t *__restrict__ chunk_term, uint32_t *__restrict__ chunk_base_keep,
               uint32_t *__restrict__ chunk_base_mark, uint32_t *__restrict__ clean_len,
               uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n_images) return;
+    const int i = img0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= img1) return;
     const ImgDev &im = imgs[i];
     uint32_t run_keep = 0, run_mark = 0;
     bool dead = false;
@@ -179,24 +219,28 @@ k_scan_chunks(const ImgDev *__restrict__ imgs, int n_images, const uint32_t *__r
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+// Writes the clean stream of one chunk: the kept bytes are compacted in shared memory (at an offset
+// congruent to their global address mod 16) and then copied out with 128-bit stores.
+__global__ void __launch_bounds__(kScanThreads, 4)
 k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
                 const uint32_t *__restrict__ chunk_img, const uint32_t *__restrict__ chunk_term,
                 const uint32_t *__restrict__ chunk_base_keep, const uint32_t *__restrict__ chunk_base_mark,
-                uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
+                uint32_t *__restrict__ seg_start, int32_t *__restrict__ status, uint32_t chunk0)
 {
     __shared__ uint32_t s_warp[kScanThreads / 32];
-    const uint32_t c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(16) uint8_t s_out[kScanChunkBytes + 32];
+    const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t base_keep = chunk_base_keep[c];
-    if (base_keep == kChunkDead) return;   // behind the end of the scan
+    if (base_keep == kChunkDead) return;   // behind the end of the scan (uniform for the CTA)
     const uint32_t img_idx = chunk_img[c];
     const ImgDev &im = imgs[img_idx];
     const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * 16u;
-    uint32_t bytes[4];
-    const ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, bytes);
-    const uint32_t live = mask_below(tid, chunk_term[c]);
-    const uint32_t keep = f.keep & live, mark = f.mark & live;
-    const uint32_t mine = __popc(keep) | (__popc(mark) << 16);
+    uint32_t w[4];
+    ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, w);
+    cut_at(chunk_term[c], tid, f.keep, f.mark);
+    const uint32_t nkeep = __popc(squeeze(f.keep));
+    const uint32_t any_mark = f.mark[0] | f.mark[1] | f.mark[2] | f.mark[3];
+    const uint32_t mine = nkeep | (__popc(squeeze(f.mark)) << 16);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -206,38 +250,82 @@ k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, co
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t before = 0;
+    uint32_t before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; w++) before += (w < (int)warp) ? s_warp[w] : 0u;
-    const uint32_t excl = before + incl - mine;
-    uint32_t out = base_keep + (excl & 0xFFFFu);       // offset in this image's clean stream
-    uint32_t rank = chunk_base_mark[c] + (excl >> 16); // ordinal of the next RSTn in the image
-    uint8_t *dst = clean + im.raw_off;
-    if (!(keep | mark)) return;
-#pragma unroll
-    for (int j = 0; j < 16; j++)
+    for (int k = 0; k < kScanThreads / 32; k++)
     {
-        const uint32_t b = (bytes[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        if ((mark >> j) & 1u)
+        const uint32_t v = s_warp[k];
+        before += (k < (int)warp) ? v : 0u;
+        total += v;
+    }
+    const uint32_t excl = before + incl - mine;
+    const uint32_t n_out = total & 0xFFFFu;                          // kept bytes of this chunk
+    const uint64_t g0 = im.raw_off + base_keep;                      // where they go in clean[]
+    const uint32_t a = (uint32_t)(g0 & 15u);
+    uint32_t lo = excl & 0xFFFFu;                                    // chunk-local output offset of this thread
+    if (nkeep == 16u)
+    {
+        uint8_t *d = s_out + a + lo;
+        if (((a + lo) & 3u) == 0u)
         {
-            if (im.has_dri && rank + 1 < im.n_segs)
-            {
-                seg_start[im.seg_first + rank + 1] = out;
-                if (b != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
-            }
-            rank++;
+#pragma unroll
+            for (int i = 0; i < 4; i++) reinterpret_cast<uint32_t *>(d)[i] = w[i];
         }
-        if ((keep >> j) & 1u) dst[out++] = (uint8_t)b;
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < 16; j++) d[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        }
+    }
+    else if (nkeep | any_mark)
+    {
+        uint32_t rank = chunk_base_mark[c] + (excl >> 16);           // ordinal of the next RSTn in the image
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+        {
+            const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (flag_at(f.mark, j))
+            {
+                if (im.has_dri && rank + 1 < im.n_segs)
+                {
+                    seg_start[im.seg_first + rank + 1] = base_keep + lo;
+                    if (b != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
+                }
+                rank++;
+            }
+            if (flag_at(f.keep, j)) s_out[a + lo++] = (uint8_t)b;
+        }
+    }
+    __syncthreads();
+    // copy out: 16-byte vectors where whole, single bytes at the two ragged ends
+    uint8_t *gd = clean + (g0 - a);
+    const uint32_t end = a + n_out;
+    for (uint32_t v = tid; v * 16u < end; v += kScanThreads)
+    {
+        const uint32_t lo16 = v * 16u;
+        if (lo16 >= a && lo16 + 16u <= end)
+            *reinterpret_cast<uint4 *>(gd + lo16) = *reinterpret_cast<const uint4 *>(s_out + lo16);
+        else
+        {
+            const uint32_t from = lo16 < a ? a : lo16, to = lo16 + 16u < end ? lo16 + 16u : end;
+            for (uint32_t k = from; k < to; k++) gd[k] = s_out[k];
+        }
     }
 }
 
 // =====================================================================================
 // Huffman decode.
+// Per-lane bit reader over the clean stream: a 64-bit big-endian window (cur:nxt) and DEPTH raw words
+// of look-ahead. A word is requested DEPTH window shifts before it is needed (it is byte-swapped only
+// when it enters the window, so the load itself never blocks). Measured on B200: a 16-byte double-
+// buffered queue hides the latency completely but costs more instructions per shift than it saves.
+template <int DEPTH>
 struct BitReader
 {
     uint32_t cur, nxt;     // big-endian words: `cur` holds the bit at `bitpos`
-    uint32_t raw2;         // the word after `nxt`, still in memory byte order (swapped when shifted in)
+    uint32_t raw[DEPTH];   // look-ahead, memory byte order; raw[0] enters the window next
     uint32_t bitpos;       // 0..31 after refill()
+    uint32_t nref;         // words shifted into the window since init()
     const uint32_t *wp;    // next word to fetch
 
     __device__ __forceinline__ void init(const uint8_t *p)
@@ -246,9 +334,11 @@ struct BitReader
         wp = reinterpret_cast<const uint32_t *>(p - a);
         cur = __byte_perm(__ldg(wp), 0, 0x0123);
         nxt = __byte_perm(__ldg(wp + 1), 0, 0x0123);
-        raw2 = __ldg(wp + 2);
-        wp += 3;
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) raw[k] = __ldg(wp + 2 + k);
+        wp += 2 + DEPTH;
         bitpos = a * 8u;
+        nref = 0u;
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
     __device__ __forceinline__ void refill()
@@ -256,36 +346,76 @@ struct BitReader
         if (bitpos >= 32u)
         {
             cur = nxt;
-            nxt = __byte_perm(raw2, 0, 0x0123);
-            raw2 = __ldg(wp);
+            nxt = __byte_perm(raw[0], 0, 0x0123);
+#pragma unroll
+            for (int k = 0; k + 1 < DEPTH; k++) raw[k] = raw[k + 1];
+            raw[DEPTH - 1] = __ldg(wp);
             wp++;
+            nref++;
             bitpos -= 32u;
         }
     }
 };
 
-// One symbol from a two-level LUT held in shared memory. Returns the leaf entry (0 = no codeword).
-__device__ __forceinline__ uint32_t lut_lookup(const uint16_t *__restrict__ tab, uint32_t peek)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Shared memory is addressed with explicit 32-bit shared-window addresses in the decode loop: with
+// generic pointers the compiler re-derives the window base (S2R SR_CgaCtaId) inside the loop.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 {
-    uint32_t e = tab[peek >> (32 - kLutBits)];
-    if (e & kLutEscape)
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+
+// One symbol from a two-level LUT in shared memory (entry format: b2j_internal.h). `tab` is the
+// shared-window byte address of the table. Returns the leaf entry, 0 when no codeword matches.
+__device__ __forceinline__ uint32_t lut_first(uint32_t tab, uint32_t pk)
+{
+    return lds_u16(tab + ((pk >> (32 - kLutBits)) << 1));
+}
+// Second level, taken when bit 5 of the first-level entry is clear (bit 5 is set in every leaf:
+// 32 + len). Returns a leaf, or 0 when the bits are no codeword.
+__device__ __forceinline__ uint32_t lut_second(uint32_t tab, uint32_t pk, uint32_t e)
+{
+    if (e != 0u)
     {
-        const uint32_t nb = e & 15u, off = (e >> 4) & 0x7FFu;
-        e = tab[(1u << kLutBits) + off + ((peek << kLutBits) >> (32u - nb))];
+        const uint32_t nb = e & 63u, off = e >> 6;
+        e = lds_u16(tab + (((1u << kLutBits) + off + ((pk << kLutBits) >> (32u - nb))) << 1));
     }
     return e;
 }
 
+// Value bits -> signed coefficient (JPEG EXTEND, decoder.cpp:72-82). v: the bits left-aligned,
+// s32 = 32 - bit count (32 -> no bits -> 0). A leading 1 bit means positive.
+__device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
+{
+    const uint32_t pos = (uint32_t)((int32_t)v >> 31);          // all ones when positive
+    const uint32_t mag = __funnelshift_rc(v ^ ~pos, 0u, s32);   // |value| (bits inverted when negative)
+    return (int32_t)((mag ^ ~pos) - ~pos);                      // negate when negative
+}
+
+template <bool WIDE, bool DEFER>
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
               const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ clean_len,
               const uint16_t *__restrict__ luts, int16_t *__restrict__ coef, int32_t *__restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    // [ per-lane block slots: kHuffThreads * 128 B ][ LUT set ]
+    // [ per-lane block slots: kHuffThreads * 128 B ][ zig-zag byte offsets: 64 B ][ LUT set ]
     uint8_t *s_slots = smem;
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128);
-    __shared__ uint8_t s_zz2[64];   // lanes sit at different scan positions: shared, not constant, memory
+    uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + 64);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -320,68 +450,89 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     // a lane whose start is unknown (missing RSTn) still emits zero blocks so the plane is defined
     const bool decodable = active && start != kSegInvalid;
 
-    BitReader br;
+    BitReader<WIDE ? 2 : 1> br;
     const uint8_t *base = clean + im.raw_off;
     br.init(base + (decodable ? start : 0u));
-    const uint32_t *wp0 = br.wp;
     const uint32_t bit0 = br.bitpos;
 
     int32_t dc0 = 0, dc1 = 0, dc2 = 0;
     int32_t err = 0;
     bool dead = !decodable;
 
-    // byte address (shared window) of this lane's slot, with the chunk swizzle folded in:
-    // coefficient n lives at slot + ((n>>3) ^ (lane&7))*16 + (n&7)*2 == (slot | lane_xor) ^ (2n)
-    const uint32_t slot_key = tid * 128u + ((lane & 7u) << 4);
+    uint32_t sm_base;   // kept opaque: otherwise the shared-window base is re-derived (S2R) inside the decode loop
+    asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_addr(smem)));
+    const uint32_t sm_zz = sm_base + kHuffThreads * 128;
+    const uint32_t sm_lut = sm_zz + 64;
+    // shared address of this lane's slot with the chunk swizzle folded in: coefficient n lives at
+    // slot + ((n>>3) ^ (lane&7))*16 + (n&7)*2 == slot_key ^ (2n)   (slots are 128-byte aligned)
+    const uint32_t slot_key = sm_base + tid * 128u + ((lane & 7u) << 4);
 
     const uint32_t max_nblk = __reduce_max_sync(0xFFFFFFFFu, nblk);
     uint32_t bi = 0;   // block index inside the MCU (uniform across the warp: segments start on MCU boundaries)
     for (uint32_t b = 0; b < max_nblk; b++)
     {
         const uint32_t comp = bi < ny ? 0u : (bi - ny + 1u);
-        const uint16_t *dc_tab = s_lut + s_lut[comp];
-        const uint16_t *ac_tab = s_lut + s_lut[3 + comp];
+        const uint32_t dc_tab = sm_lut + 2u * (uint32_t)s_lut[comp];
+        const uint32_t ac_tab = sm_lut + 2u * (uint32_t)s_lut[3 + comp];
         const bool mine = b < nblk;
         if (mine && !dead)
         {
             // ---- DC (decoder.cpp:226-233)
             uint32_t pk = br.peek();
-            uint32_t e = lut_lookup(dc_tab, pk);
-            uint32_t len = e & 31u, size = (e >> 5) & 31u;
-            if (len == 0) { err |= B2J_ST_BAD_CODE; dead = true; }
+            uint32_t e = lut_first(dc_tab, pk);
+            if (!(e & 32u)) e = lut_second(dc_tab, pk, e);
+            if (!(e & 32u)) { err |= B2J_ST_BAD_CODE; dead = true; }
             else
             {
-                const int32_t diff = extend_top(pk << len, (int)size);
-                br.bitpos += len + size;
+                uint32_t lenx = e & 63u, s32 = (e >> 6) & 63u;
+                const int32_t diff = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
+                br.bitpos += lenx - s32;      // (32 + len) - (32 - size)
                 br.refill();
                 int32_t dcv;
                 if (comp == 0) { dc0 += diff; dcv = dc0; }
                 else if (comp == 1) { dc1 += diff; dcv = dc1; }
                 else { dc2 += diff; dcv = dc2; }
                 if (dcv != (int32_t)(int16_t)dcv) err |= B2J_ST_DC_RANGE;
-                *reinterpret_cast<int16_t *>(s_slots + slot_key) = (int16_t)dcv;
-                // ---- AC (decoder.cpp:236-258)
-                uint32_t pos = 1;
-                bool eob = false;
-                while (pos < 64u)
+                sts_u16(slot_key, (uint32_t)dcv);
+                // ---- AC (decoder.cpp:236-258). The store of coefficient i is issued one iteration late, behind
+                // the table lookup of symbol i+1: its zig-zag lookup then never stalls the in-order warp.
+                uint32_t pos = 1, pend_zz = 0, pend_v = 0;
+                bool pend = false;
+                while (true)
                 {
                     pk = br.peek();
-                    e = lut_lookup(ac_tab, pk);
-                    len = e & 31u;
-                    if (len == 0) { err |= B2J_ST_BAD_CODE; dead = true; eob = true; break; }
-                    size = (e >> 5) & 31u;
-                    const uint32_t run = (e >> 10) & 15u;
-                    const int32_t v = extend_top(pk << len, (int)size);
-                    br.bitpos += len + size;
-                    pos += run;
-                    if ((e >> 5) == 0u) { eob = true; break; }   // run == 0 && size == 0
-                    if (size != 0u && pos < 64u)
-                        *reinterpret_cast<int16_t *>(s_slots + (slot_key ^ (uint32_t)s_zz2[pos])) = (int16_t)v;
-                    pos++;   // past the stored coefficient, or the extra zero of a size-0 run (decoder.cpp:247-252)
+                    e = lut_first(ac_tab, pk);
+                    if (DEFER)
+                    {
+                        if (pend) sts_u16(slot_key ^ pend_zz, pend_v);
+                        pend = false;
+                    }
+                    if (!(e & 32u))
+                    {
+                        e = lut_second(ac_tab, pk, e);
+                        if (!(e & 32u)) { err |= B2J_ST_BAD_CODE; dead = true; break; }
+                    }
+                    lenx = e & 63u;
+                    const uint32_t rs = e >> 6;            // run << 6 | (32 - size)
+                    s32 = rs & 63u;
+                    const int32_t v = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
+                    br.bitpos += lenx - s32;
                     br.refill();
+                    if (rs == 32u) break;                   // run == 0 && size == 0: EOB
+                    pos += e >> 12;
+                    if (s32 != 32u && pos < 64u)
+                    {
+                        if (DEFER) { pend_zz = lds_u8(sm_zz + pos); pend_v = (uint32_t)v; pend = true; }
+                        else sts_u16(slot_key ^ lds_u8(sm_zz + pos), (uint32_t)v);
+                    }
+                    pos++;   // past the stored coefficient, or the extra zero of a size-0 run (decoder.cpp:247-252)
+                    if (pos >= 64u)
+                    {
+                        if (pos > 64u) { err |= B2J_ST_BLOCK_OVERFLOW; dead = true; }   // decoder.cpp:259
+                        break;
+                    }
                 }
-                if (eob) br.refill();
-                else if (pos > 64u) { err |= B2J_ST_BLOCK_OVERFLOW; dead = true; }   // decoder.cpp:259
+                if (DEFER && pend) sts_u16(slot_key ^ pend_zz, pend_v);
             }
         }
         __syncwarp();
@@ -410,7 +561,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         // bits consumed since `start`; a restart interval must end exactly at its marker
         // (decoder.cpp:296-302 aligns to the byte boundary and expects RSTn there)
-        const uint64_t bits = (uint64_t)(br.wp - wp0) * 32u + br.bitpos - bit0;
+        const uint64_t bits = (uint64_t)br.nref * 32u + br.bitpos - bit0;
         const uint64_t used = (bits + 7u) >> 3;
         const uint64_t avail = (uint64_t)end - start;
         if (used > avail) err |= B2J_ST_OVERRUN;
@@ -454,52 +605,13 @@ __device__ __forceinline__ uint32_t addclamp2(uint32_t a, uint32_t b)
     return __viaddmin_s16x2_relu(a, b, 0x00FF00FFu);
 }
 
-// Converts RV rows x 4 pixels. y2[r][0..1]: packed int16 luma pairs of row r; cb2/cr2: the chroma
-// samples of the two pixel pairs (already replicated horizontally) as packed pairs. Writes the
-// 4 BGRA words per row.
-template <int RH, int RV>
-__device__ __forceinline__ void csc_rows(const uint32_t (*y2)[2], const uint32_t cb2[2], const uint32_t cr2[2], uint32_t (*out)[4])
+// int32 pair -> int16 pair with saturation, then the reference's clip to [-256,255] on both halves
+// (cpuIDCT8x8.cpp:13-23). Saturating to int16 first cannot change a value that is clipped to 9 bits.
+__device__ __forceinline__ uint32_t pack_clip2(int32_t lo, int32_t hi)
 {
-#pragma unroll
-    for (int h = 0; h < 2; h++)   // pixel pairs (0,1) and (2,3)
-    {
-        const int32_t u0 = (int16_t)(cb2[h] & 0xFFFFu), u1 = (int32_t)cb2[h] >> 16;
-        const int32_t v0 = (int16_t)(cr2[h] & 0xFFFFu), v1 = (int32_t)cr2[h] >> 16;
-        uint32_t ro, go, bo;
-        bool special;
-        if (RH == 2)
-        {   // both pixels of the pair share one chroma sample
-            ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) * 0x10001u;
-            go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) * 0x10001u;
-            bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) * 0x10001u;
-            special = (u0 == -200 && v0 == 200);
-        }
-        else
-        {
-            ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) | ((uint32_t)csc_r_off(v1) << 16);
-            go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) | ((uint32_t)csc_g_off(u1, v1) << 16);
-            bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) | ((uint32_t)csc_b_off(u1) << 16);
-            special = (u0 == -200 && v0 == 200) || (u1 == -200 && v1 == 200);
-        }
-#pragma unroll
-        for (int r = 0; r < RV; r++)
-        {
-            const uint32_t yy = y2[r][h];
-            const uint32_t R = addclamp2(yy, ro), B = addclamp2(yy, bo);
-            uint32_t G = addclamp2(yy, go);
-            if (special)
-            {
-                // the one double-rounding case of the reference (see b2j_math.h)
-                const int32_t ya = (int16_t)(yy & 0xFFFFu), yb = (int32_t)yy >> 16;
-                const uint32_t ga = clamp255(ya + csc_g_off(u0, v0) - csc_g_fix(ya, u0, v0));
-                const uint32_t gb = clamp255(yb + csc_g_off(u1, v1) - csc_g_fix(yb, u1, v1));
-                G = ga | (gb << 16);
-            }
-            const uint32_t bg = __byte_perm(B, G, 0x6240);          // B0 G0 B1 G1
-            out[r][2 * h + 0] = __byte_perm(bg, R, 0x5410);         // B0 G0 R0 0
-            out[r][2 * h + 1] = __byte_perm(bg, R, 0x7632);         // B1 G1 R1 0
-        }
-    }
+    uint32_t d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return __vmins2(__vmaxs2(d, 0xFF00FF00u), 0x00FF00FFu);
 }
 
 // Layout constants of a tile for luma sampling RH x RV (chroma 1x1):
@@ -512,202 +624,326 @@ struct TileGeom
     static constexpr uint32_t mcu_w = 8 * RH, mcu_h = 8 * RV;
     static constexpr uint32_t mcus = kTileBlocks / tot;   // MCUs per tile
     static constexpr uint32_t xg = mcu_w / 4;             // 4-pixel groups per MCU row
+    static constexpr uint32_t cols = mcus * xg;           // 4-pixel columns per tile: 128, 128, 192, 96
 };
 
+constexpr uint32_t kQtStride = 68;       // words between the per-component quantiser tables: 64 + 4, so that
+                                         // the three tables start in different 16-byte bank groups
+
+// What the transform and the colour phase need to know about a tile, staged in shared memory one
+// iteration ahead (persistent kernel) so that no global load sits between two tiles.
+struct TileSide
+{
+    alignas(16) uint32_t qt[3 * kQtStride];   // quantisers, natural order, widened to 32 bit
+    uint2 mcu_xy[kTileBlocks / 3];            // MCU coordinates inside the image
+    uint8_t *pix;                             // first byte of the image in the pixel plane
+    uint32_t width, height;
+    uint32_t mode, n_mcus;
+};
+
+struct TileSmem
+{
+    // coefficient tile: kTileBlocks rows of 128 B each; the 16-byte chunk c of row r sits at chunk
+    // c ^ (r & 7) (the TMA SWIZZLE_128B pattern; the non-TMA variant stores with the same XOR)
+    alignas(1024) uint8_t tile[1][kTileBlocks * 128];
+    TileSide side[1];
+    alignas(8) uint64_t bar[1];
+};
+
+// Chroma offsets of one pixel pair, packed as two int16: the pair shares one sample when RH == 2.
+template <int RH>
+__device__ __forceinline__ void chroma_offsets(uint32_t cb, uint32_t cr, uint32_t &ro, uint32_t &go, uint32_t &bo, bool &special)
+{
+    const int32_t u0 = (int16_t)(cb & 0xFFFFu), v0 = (int16_t)(cr & 0xFFFFu);
+    if (RH == 2)
+    {
+        ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) * 0x10001u;
+        go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) * 0x10001u;
+        bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) * 0x10001u;
+        special = ((cb & 0xFFFFu) == 0xFF38u) & ((cr & 0xFFFFu) == 0x00C8u);   // U = -200, V = 200
+    }
+    else
+    {
+        const int32_t u1 = (int32_t)cb >> 16, v1 = (int32_t)cr >> 16;
+        ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) | ((uint32_t)csc_r_off(v1) << 16);
+        go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) | ((uint32_t)csc_g_off(u1, v1) << 16);
+        bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) | ((uint32_t)csc_b_off(u1) << 16);
+        special = (((cb & 0xFFFFu) == 0xFF38u) & ((cr & 0xFFFFu) == 0x00C8u)) | (((cb >> 16) == 0xFF38u) & ((cr >> 16) == 0x00C8u));
+    }
+}
+
+// The one double-rounding case of the reference (b2j_math.h): recompute G of a pixel pair the slow way.
+__device__ __noinline__ uint32_t green_special(uint32_t yy, uint32_t cb, uint32_t cr)
+{
+    const int32_t ya = (int16_t)(yy & 0xFFFFu), yb = (int32_t)yy >> 16;
+    const int32_t u0 = (int16_t)(cb & 0xFFFFu), u1 = (int32_t)cb >> 16;
+    const int32_t v0 = (int16_t)(cr & 0xFFFFu), v1 = (int32_t)cr >> 16;
+    const uint32_t ga = clamp255(ya + csc_g_off(u0, v0) - csc_g_fix(ya, u0, v0));
+    const uint32_t gb = clamp255(yb + csc_g_off(u1, v1) - csc_g_fix(yb, u1, v1));
+    return ga | (gb << 16);
+}
+
+// Colour work of one 4-pixel column of the tile for row groups [rg0, rg1) (every layout has 8 row
+// groups per MCU: mcu_h / RV == 8); a work item is 4 pixels x RV rows (one chroma row). Consecutive
+// threads are consecutive along x, so every store instruction writes 512 contiguous bytes per warp.
 template <int RH, int RV>
-__device__ __forceinline__ void csc_phase(const uint8_t *__restrict__ s_tile, const uint2 *__restrict__ s_mcu_xy,
-                                          const ImgDev &im, uint32_t n_mcus, uint8_t *__restrict__ pix, uint32_t tid)
+__device__ __forceinline__ void csc_column(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t col, uint32_t rg0, uint32_t rg1)
 {
     using G = TileGeom<RH, RV>;
-    // work item = 4 pixels x RV rows; consecutive threads walk along x through the MCUs of the tile,
-    // then down the 8 row groups every layout has (mcu_h / RV == 8)
-    const uint32_t per_rg = n_mcus * G::xg;
-    const bool vec_ok = (im.width & 3u) == 0u;
-    uint32_t rg = 0, rem = tid;
-    while (true)
+    if (col >= sd.n_mcus * G::xg) return;
+    const uint32_t width = sd.width, height = sd.height;
+    const uint32_t m = col / G::xg, x4 = col % G::xg;
+    const uint2 mxy = sd.mcu_xy[m];
+    const uint32_t xin = x4 * 4u;
+    const uint32_t px = mxy.x * G::mcu_w + xin;
+    const uint32_t py_top = mxy.y * G::mcu_h;
+    if (px >= width) return;
+    const bool vec_ok = (width & 3u) == 0u;   // then the 4-pixel group is whole and 16-byte aligned
+    const size_t pitch = (size_t)width * 4u;
+    uint8_t *dst = sd.pix + ((size_t)py_top * width + px) * 4u;
+    const uint32_t row0 = m * G::tot;
+    // shared-memory addresses: luma block column and chroma blocks of this thread never change
+    const uint32_t ycol = (xin >> 3), yoff = (xin & 7u) * 2u;
+    const uint32_t brow = row0 + G::ny, rrow = brow + 1u;
+    const uint32_t cxo = (xin / RH) * 2u;
+    const uint8_t *cbp = s_tile + brow * 128u + cxo, *crp = s_tile + rrow * 128u + cxo;
+    const uint32_t bsw = brow & 7u, rsw = rrow & 7u;
+#pragma unroll 1
+    for (uint32_t rg = rg0; rg < rg1; rg++)
     {
-        while (rem >= per_rg) { rem -= per_rg; rg++; }
-        if (rg >= 8u) break;
-        const uint32_t m = rem / G::xg, x4 = rem % G::xg;
-        const uint2 mxy = s_mcu_xy[m];
-        const uint32_t xin = x4 * 4u, yin0 = rg * RV;
-        const uint32_t px = mxy.x * G::mcu_w + xin;
-        const uint32_t py0 = mxy.y * G::mcu_h + yin0;
-        rem += kTileBlocks;
-        if (px >= im.width || py0 >= im.height) continue;
-        const uint32_t row0 = m * G::tot;
-        // luma
-        uint32_t y2[RV][2];
-#pragma unroll
-        for (int r = 0; r < RV; r++)
-        {
-            const uint32_t yin = yin0 + r;
-            const uint32_t srow = row0 + (yin >> 3) * G::yh + (xin >> 3);
-            const uint32_t off = srow * 128u + (((yin & 7u) ^ (srow & 7u)) << 4) + (xin & 7u) * 2u;
-            const uint2 v = *reinterpret_cast<const uint2 *>(s_tile + off);
-            y2[r][0] = v.x; y2[r][1] = v.y;
-        }
-        // chroma (pixel replication, decoder.cpp:478-480)
+        if (py_top + rg * RV >= height) break;
+        // chroma (pixel replication, decoder.cpp:478-480): row rg of the Cb / Cr block
         uint32_t cb2[2], cr2[2];
+        if (RH == 2)
         {
-            const uint32_t cx = xin / RH, cy = rg;   // yin / RV == rg in every layout
-            const uint32_t brow = row0 + G::ny, rrow = brow + 1u;
-            const uint32_t boff = brow * 128u + ((cy ^ (brow & 7u)) << 4) + cx * 2u;
-            const uint32_t roff = rrow * 128u + ((cy ^ (rrow & 7u)) << 4) + cx * 2u;
-            if (RH == 2)
-            {
-                const uint32_t b = *reinterpret_cast<const uint32_t *>(s_tile + boff);
-                const uint32_t r = *reinterpret_cast<const uint32_t *>(s_tile + roff);
-                cb2[0] = __byte_perm(b, 0, 0x1010); cb2[1] = __byte_perm(b, 0, 0x3232);
-                cr2[0] = __byte_perm(r, 0, 0x1010); cr2[1] = __byte_perm(r, 0, 0x3232);
-            }
-            else
-            {
-                const uint2 b = *reinterpret_cast<const uint2 *>(s_tile + boff);
-                const uint2 r = *reinterpret_cast<const uint2 *>(s_tile + roff);
-                cb2[0] = b.x; cb2[1] = b.y; cr2[0] = r.x; cr2[1] = r.y;
-            }
+            const uint32_t b = *reinterpret_cast<const uint32_t *>(cbp + ((rg ^ bsw) << 4));
+            const uint32_t r = *reinterpret_cast<const uint32_t *>(crp + ((rg ^ rsw) << 4));
+            cb2[0] = b & 0xFFFFu; cb2[1] = b >> 16; cr2[0] = r & 0xFFFFu; cr2[1] = r >> 16;
         }
-        uint32_t out[RV][4];
-        csc_rows<RH, RV>(y2, cb2, cr2, out);
+        else
+        {
+            const uint2 b = *reinterpret_cast<const uint2 *>(cbp + ((rg ^ bsw) << 4));
+            const uint2 r = *reinterpret_cast<const uint2 *>(crp + ((rg ^ rsw) << 4));
+            cb2[0] = b.x; cb2[1] = b.y; cr2[0] = r.x; cr2[1] = r.y;
+        }
+        uint32_t ro[2], go[2], bo[2];
+        bool sp[2];
+        chroma_offsets<RH>(cb2[0], cr2[0], ro[0], go[0], bo[0], sp[0]);
+        chroma_offsets<RH>(cb2[1], cr2[1], ro[1], go[1], bo[1], sp[1]);
 #pragma unroll
         for (int r = 0; r < RV; r++)
         {
-            const uint32_t py = py0 + r;
-            if (py >= im.height) break;
-            uint8_t *dst = pix + im.pix_off + ((size_t)py * im.width + px) * 4u;
-            if (vec_ok)   // width % 4 == 0 -> the group is whole and 16-byte aligned
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(out[r][0], out[r][1], out[r][2], out[r][3]);
+            const uint32_t yin = rg * RV + (uint32_t)r;
+            if (r > 0 && py_top + yin >= height) break;
+            const uint32_t srow = row0 + (yin >> 3) * G::yh + ycol;
+            const uint2 yv = *reinterpret_cast<const uint2 *>(s_tile + srow * 128u + (((yin & 7u) ^ (srow & 7u)) << 4) + yoff);
+            const uint32_t y2[2] = {yv.x, yv.y};
+            uint32_t out[4];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                const uint32_t R = addclamp2(y2[h], ro[h]), B = addclamp2(y2[h], bo[h]);
+                uint32_t Gc = addclamp2(y2[h], go[h]);
+                if (__builtin_expect(sp[h], 0))
+                    Gc = green_special(y2[h], RH == 2 ? cb2[h] * 0x10001u : cb2[h], RH == 2 ? cr2[h] * 0x10001u : cr2[h]);
+                const uint32_t bg = __byte_perm(B, Gc, 0x6240);     // B0 G0 B1 G1
+                out[2 * h + 0] = __byte_perm(bg, R, 0x5410);        // B0 G0 R0 0
+                out[2 * h + 1] = __byte_perm(bg, R, 0x7632);        // B1 G1 R1 0
+            }
+            uint8_t *d = dst + (size_t)yin * pitch;
+            if (vec_ok)
+                *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
             else
             {
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (px + k < im.width) reinterpret_cast<uint32_t *>(dst)[k] = out[r][k];
+                    if (px + k < width) reinterpret_cast<uint32_t *>(d)[k] = out[k];
             }
         }
     }
 }
 
-struct TileSmem
+// Colour phase: the tile's (columns x 8 row groups) work items spread evenly over all 192 threads.
+template <int RH, int RV>
+__device__ __forceinline__ void csc_phase(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t tid)
 {
-    // coefficient tile: kTileBlocks rows of 128 B; the 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-    // (the TMA SWIZZLE_128B pattern; the non-TMA variant stores with the same XOR)
-    alignas(1024) uint8_t tile[kTileBlocks * 128];
-    alignas(16) uint16_t qt[3][64];
-    uint2 mcu_xy[kTileBlocks / 3];
-    alignas(8) uint64_t bar;
-};
+    using G = TileGeom<RH, RV>;
+    if (G::cols == 192) csc_column<RH, RV>(s_tile, sd, tid, 0, 8);                                  // 4:2:2: 8 items each
+    else if (G::cols == 96) csc_column<RH, RV>(s_tile, sd, tid % 96u, (tid / 96u) * 4u, (tid / 96u) * 4u + 4u);   // 4:4:0: 4 each
+    else if (tid < 128) csc_column<RH, RV>(s_tile, sd, tid, 0, 5);                                  // 128 columns: 5 items ...
+    else
+    {
+        csc_column<RH, RV>(s_tile, sd, tid - 128u, 5, 8);                                           // ... or 2 x 3 items
+        csc_column<RH, RV>(s_tile, sd, tid - 64u, 5, 8);
+    }
+}
 
-template <int RH, int RV, bool USE_TMA>
-__device__ __forceinline__ void tile_body(TileSmem &sm, const CUtensorMap *tmap, const int16_t *__restrict__ coef, const ImgDev &im,
-                                          const TileDev tile, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix,
-                                          int32_t *__restrict__ status)
+// Dynamic shared memory (> 48 KB), rounded up to the 1024-byte alignment SWIZZLE_128B needs.
+constexpr size_t kTileSmemBytes = sizeof(TileSmem) + 1024;
+__device__ __forceinline__ TileSmem *tile_smem()
+{
+    extern __shared__ uint8_t dyn_smem[];
+    const uint32_t a = smem_addr(dyn_smem);
+    return reinterpret_cast<TileSmem *>(dyn_smem + ((1024u - (a & 1023u)) & 1023u));
+}
+
+// Dequantise + IDCT of one block per thread, in place in the swizzled tile (decoder.cpp:340,
+// cpuIDCT8x8.cpp:25-127).
+template <int RH, int RV>
+__device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const TileSide &sd)
 {
     using G = TileGeom<RH, RV>;
     const uint32_t tid = threadIdx.x;
-    const uint32_t row_first = im.blk_first + tile.mcu_first * G::tot;
-    const uint32_t n_mcus = min(G::mcus, im.mcu_count - tile.mcu_first);
+    const uint32_t bi = tid % G::tot;
+    const uint32_t comp = bi < G::ny ? 0u : (bi - G::ny + 1u);
+    const uint32_t *q = sd.qt + comp * kQtStride;
+    uint8_t *rowp = tilep + tid * 128u;
+    const uint32_t sw = tid & 7u;
+    int32_t v[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        const uint4 cw = *reinterpret_cast<const uint4 *>(rowp + ((r ^ sw) << 4));
+        const uint4 qa = *reinterpret_cast<const uint4 *>(q + 8 * r);
+        const uint4 qb = *reinterpret_cast<const uint4 *>(q + 8 * r + 4);
+        // decoder.cpp:340: int32 product of the decoded value and the quantiser
+        v[8 * r + 0] = (int32_t)(int16_t)(cw.x & 0xFFFFu) * (int32_t)qa.x;
+        v[8 * r + 1] = ((int32_t)cw.x >> 16) * (int32_t)qa.y;
+        v[8 * r + 2] = (int32_t)(int16_t)(cw.y & 0xFFFFu) * (int32_t)qa.z;
+        v[8 * r + 3] = ((int32_t)cw.y >> 16) * (int32_t)qa.w;
+        v[8 * r + 4] = (int32_t)(int16_t)(cw.z & 0xFFFFu) * (int32_t)qb.x;
+        v[8 * r + 5] = ((int32_t)cw.z >> 16) * (int32_t)qb.y;
+        v[8 * r + 6] = (int32_t)(int16_t)(cw.w & 0xFFFFu) * (int32_t)qb.z;
+        v[8 * r + 7] = ((int32_t)cw.w >> 16) * (int32_t)qb.w;
+        idct_row(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        idct_col_noclip(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        uint4 o;
+        o.x = pack_clip2(v[8 * r + 0], v[8 * r + 1]);
+        o.y = pack_clip2(v[8 * r + 2], v[8 * r + 3]);
+        o.z = pack_clip2(v[8 * r + 4], v[8 * r + 5]);
+        o.w = pack_clip2(v[8 * r + 6], v[8 * r + 7]);
+        *reinterpret_cast<uint4 *>(rowp + ((r ^ sw) << 4)) = o;
+    }
+}
 
+__device__ __forceinline__ void idct_dispatch(uint8_t *tilep, const TileSide &sd)
+{
+    switch (sd.mode)   // uniform per CTA
+    {
+    case kMode444: idct_phase<1, 1>(tilep, sd); break;
+    case kMode420: idct_phase<2, 2>(tilep, sd); break;
+    case kMode422: idct_phase<2, 1>(tilep, sd); break;
+    default:       idct_phase<1, 2>(tilep, sd); break;
+    }
+}
+
+// chroma replication + colour + store (decoder.cpp:443-495, 367-370)
+__device__ __forceinline__ void csc_dispatch(const uint8_t *tilep, const TileSide &sd)
+{
+    const uint32_t tid = threadIdx.x;
+    switch (sd.mode)
+    {
+    case kMode444: csc_phase<1, 1>(tilep, sd, tid); break;
+    case kMode420: csc_phase<2, 2>(tilep, sd, tid); break;
+    case kMode422: csc_phase<2, 1>(tilep, sd, tid); break;
+    default:       csc_phase<1, 2>(tilep, sd, tid); break;
+    }
+}
+
+// Side data of a tile, in two halves so that the global loads of the first half can fly while the
+// previous tile is being transformed.
+struct SideRegs { uint32_t q, width, height, mcu_count_w; uint64_t pix_off; };
+
+__device__ __forceinline__ SideRegs side_load(const ImgDev *__restrict__ imgs, const uint16_t *__restrict__ qtabs, const TileDev d)
+{
+    SideRegs r;
+    const ImgDev *im = imgs + d.img;
+    r.q = (uint32_t)__ldg(qtabs + (size_t)d.img * 192 + threadIdx.x);
+    r.width = __ldg(&im->width);
+    r.height = __ldg(&im->height);
+    r.mcu_count_w = __ldg(&im->mcu_count_w);
+    r.pix_off = __ldg(reinterpret_cast<const unsigned long long *>(&im->pix_off));
+    return r;
+}
+
+__device__ __forceinline__ void side_store(TileSide &sd, const TileDev d, const SideRegs &r, uint8_t *__restrict__ pix)
+{
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_mcus = d.info >> 8;
+    sd.qt[(tid >> 6) * kQtStride + (tid & 63u)] = r.q;
+    if (tid < n_mcus)
+    {
+        const uint32_t gm = d.mcu_first + tid;
+        const uint32_t my = gm / r.mcu_count_w;
+        sd.mcu_xy[tid] = make_uint2(gm - my * r.mcu_count_w, my);
+    }
+    if (tid == 0)
+    {
+        sd.pix = pix + r.pix_off;
+        sd.width = r.width; sd.height = r.height;
+        sd.mode = d.info & 0xFFu; sd.n_mcus = n_mcus;
+    }
+}
+
+__device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMode444 ? 3u : (mode == kMode420 ? 6u : 4u); }
+
+// One tile per CTA. USE_TMA: the 24 KB coefficient tile arrives by one TMA tensor load (128-byte
+// swizzle, mbarrier completion) issued by thread 0 while the other threads fetch the side data;
+// otherwise (B2J_USE_TMA=0) plain 128-bit loads store into the same swizzled layout.
+// Measured on B200 (profiles/): a persistent double-buffered variant and a warp-autonomous variant of
+// this kernel were both slower -- the kernel is bound by dependent-issue latency at 24 warps per SM,
+// not by the latency in front of a tile, so the simplest structure wins.
+template <bool USE_TMA>
+__global__ void __launch_bounds__(kTileBlocks, 4)
+k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
+           const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
+{
+    TileSmem &sm = *tile_smem();
+    const uint32_t tid = threadIdx.x;
+    const TileDev d = tiles[blockIdx.x];
     if (USE_TMA)
     {
         if (tid == 0)
         {
-            mbar_init(&sm.bar, 1);
+            mbar_init(&sm.bar[0], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&sm.bar[0], kTileBlocks * 128);
+            tma_load_2d(sm.tile[0], &tmap, 0, (int)d.row_first, &sm.bar[0]);
         }
-        __syncthreads();
-        if (tid == 0)
+        side_store(sm.side[0], d, side_load(imgs, qtabs, d), pix);
+        __syncthreads();   // barrier initialisation + side data visible
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&sm.bar[0], 0))
         {
-            mbar_expect_tx(&sm.bar, kTileBlocks * 128);
-            tma_load_2d(sm.tile, tmap, 0, (int)row_first, &sm.bar);
+            if (++spins > (1u << 22)) { if (tid == 0) atomicOr(&status[d.img], 0x4000); break; }   // never hang the GPU
         }
     }
     else
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(coef + (size_t)row_first * 64);
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + (size_t)d.row_first * 64);
         uint4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = __ldg(src + (uint32_t)k * kTileBlocks + tid);   // the plane is padded by one tile
+        const SideRegs r = side_load(imgs, qtabs, d);
 #pragma unroll
         for (int k = 0; k < 8; k++)
         {
             const uint32_t idx = (uint32_t)k * kTileBlocks + tid;   // 16-byte granule: row = idx>>3, chunk = idx&7
-            const uint32_t r = idx >> 3, c = idx & 7u;
-            *reinterpret_cast<uint4 *>(sm.tile + r * 128u + ((c ^ (r & 7u)) << 4)) = v[k];
+            const uint32_t rr = idx >> 3, c = idx & 7u;
+            *reinterpret_cast<uint4 *>(sm.tile[0] + rr * 128u + ((c ^ (rr & 7u)) << 4)) = v[k];
         }
+        side_store(sm.side[0], d, r, pix);
+        __syncthreads();
     }
-    // quantisers (natural order, per component) and MCU coordinates while the tile is in flight
-    if (tid < 96) reinterpret_cast<uint32_t *>(&sm.qt[0][0])[tid] = __ldg(reinterpret_cast<const uint32_t *>(qtabs + (size_t)tile.img * 192) + tid);
-    if (tid < n_mcus)
-    {
-        const uint32_t gm = tile.mcu_first + tid;
-        const uint32_t my = gm / im.mcu_count_w;
-        sm.mcu_xy[tid] = make_uint2(gm - my * im.mcu_count_w, my);
-    }
-    if (USE_TMA)
-    {
-        uint32_t spins = 0;
-        while (!mbar_try_wait(&sm.bar, 0))
-        {
-            if (++spins > (1u << 22)) { if (tid == 0) atomicOr(&status[tile.img], 0x4000); break; }   // never hang the GPU
-        }
-    }
+    idct_dispatch(sm.tile[0], sm.side[0]);
     __syncthreads();
-
-    // ---- thread-per-block dequantise + IDCT, in place (decoder.cpp:340, cpuIDCT8x8.cpp:25-127)
-    {
-        const uint32_t bi = tid % G::tot;
-        const uint32_t comp = bi < G::ny ? 0u : (bi - G::ny + 1u);
-        const uint16_t *q = sm.qt[comp];
-        uint8_t *rowp = sm.tile + tid * 128u;
-        const uint32_t sw = tid & 7u;
-        int32_t v[64];
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-        {
-            const uint4 cw = *reinterpret_cast<const uint4 *>(rowp + ((r ^ sw) << 4));
-            const uint4 qw = *reinterpret_cast<const uint4 *>(q + 8 * r);
-            const uint32_t c4[4] = {cw.x, cw.y, cw.z, cw.w}, q4[4] = {qw.x, qw.y, qw.z, qw.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                v[8 * r + 2 * k + 0] = (int32_t)(int16_t)(c4[k] & 0xFFFFu) * (int32_t)(q4[k] & 0xFFFFu);
-                v[8 * r + 2 * k + 1] = ((int32_t)c4[k] >> 16) * (int32_t)(q4[k] >> 16);
-            }
-        }
-        idct_8x8(v);
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-        {
-            uint4 o;
-            o.x = (uint32_t)(v[8 * r + 0] & 0xFFFF) | ((uint32_t)v[8 * r + 1] << 16);
-            o.y = (uint32_t)(v[8 * r + 2] & 0xFFFF) | ((uint32_t)v[8 * r + 3] << 16);
-            o.z = (uint32_t)(v[8 * r + 4] & 0xFFFF) | ((uint32_t)v[8 * r + 5] << 16);
-            o.w = (uint32_t)(v[8 * r + 6] & 0xFFFF) | ((uint32_t)v[8 * r + 7] << 16);
-            *reinterpret_cast<uint4 *>(rowp + ((r ^ sw) << 4)) = o;
-        }
-    }
-    __syncthreads();
-
-    // ---- chroma replication + colour + store (decoder.cpp:443-495, 367-370)
-    csc_phase<RH, RV>(sm.tile, sm.mcu_xy, im, n_mcus, pix, tid);
-}
-
-template <bool USE_TMA>
-__global__ void __launch_bounds__(kTileBlocks)
-k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
-           const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
-{
-    __shared__ TileSmem sm;
-    const TileDev tile = tiles[blockIdx.x];
-    const ImgDev &im = imgs[tile.img];
-    switch (im.mode)   // uniform per CTA
-    {
-    case kMode444: tile_body<1, 1, USE_TMA>(sm, &tmap, coef, im, tile, qtabs, pix, status); break;
-    case kMode420: tile_body<2, 2, USE_TMA>(sm, &tmap, coef, im, tile, qtabs, pix, status); break;
-    case kMode422: tile_body<2, 1, USE_TMA>(sm, &tmap, coef, im, tile, qtabs, pix, status); break;
-    default:       tile_body<1, 2, USE_TMA>(sm, &tmap, coef, im, tile, qtabs, pix, status); break;
-    }
+    csc_dispatch(sm.tile[0], sm.side[0]);
 }
 
 // =====================================================================================
@@ -726,37 +962,58 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
 
 // =====================================================================================
 // Launchers (host).
-size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128 + (size_t)max_lut_len * 2; }
+size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128 + 64 + (size_t)max_lut_len * 2; }
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {
-    return cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_huff_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_huff_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_huff_decode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_idct_csc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_idct_csc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
 }
 
-void launch_prepass(const DecodeArgs &a, cudaStream_t s)
+void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
-    if (a.n_chunks == 0) return;
-    k_scan_count<<<a.n_chunks, kScanThreads, 0, s>>>(a.raw, a.imgs, a.chunk_img, a.chunk_cnt, a.chunk_term);
-    k_scan_chunks<<<(a.n_images + 3) / 4, 128, 0, s>>>(a.imgs, a.n_images, a.chunk_cnt, a.chunk_term, a.chunk_base_keep,
-                                                       a.chunk_base_mark, a.clean_len, a.seg_start, a.status);
-    k_unstuff_write<<<a.n_chunks, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_term, a.chunk_base_keep,
-                                                        a.chunk_base_mark, a.seg_start, a.status);
+    const uint32_t nc = r.chunk1 - r.chunk0, ni = r.img1 - r.img0;
+    if (nc == 0 || ni == 0) return;
+    k_scan_count<<<nc, kScanThreads, 0, s>>>(a.raw, a.imgs, a.chunk_img, a.chunk_cnt, a.chunk_term, r.chunk0);
+    k_scan_chunks<<<(ni + 3) / 4, 128, 0, s>>>(a.imgs, (int)r.img0, (int)r.img1, a.chunk_cnt, a.chunk_term, a.chunk_base_keep,
+                                               a.chunk_base_mark, a.clean_len, a.seg_start, a.status);
+    k_unstuff_write<<<nc, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_term, a.chunk_base_keep,
+                                                a.chunk_base_mark, a.seg_start, a.status, r.chunk0);
 }
 
-void launch_huffman(const DecodeArgs &a, cudaStream_t s)
+void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
-    if (a.n_huff_ctas == 0) return;
-    k_huff_decode<<<a.n_huff_ctas, kHuffThreads, huff_smem_bytes(a.max_lut_len), s>>>(a.clean, a.imgs, a.huff_ctas, a.seg_start,
-                                                                                      a.clean_len, a.luts, a.coef, a.status);
+    const uint32_t n = r.cta1 - r.cta0;
+    if (n == 0) return;
+    const size_t sm = huff_smem_bytes(a.max_lut_len);
+#define B2J_HUFF_LAUNCH(W, D) k_huff_decode<W, D><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts, a.coef, a.status)
+    switch (a.huff_variant & 3u)
+    {
+    case 0: B2J_HUFF_LAUNCH(false, false); break;
+    case 1: B2J_HUFF_LAUNCH(true, false); break;
+    case 2: B2J_HUFF_LAUNCH(false, true); break;
+    default: B2J_HUFF_LAUNCH(true, true); break;
+    }
+#undef B2J_HUFF_LAUNCH
 }
 
-void launch_idct(const DecodeArgs &a, cudaStream_t s)
+void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
-    if (a.n_tiles == 0) return;
+    const uint32_t n = r.tile1 - r.tile0;
+    if (n == 0) return;
     if (a.use_tma)
-        k_idct_csc<true><<<a.n_tiles, kTileBlocks, 0, s>>>(*a.tmap, a.coef, a.imgs, a.tiles, a.qtabs, a.pixels, a.status);
+        k_idct_csc<true><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status);
     else
-        k_idct_csc<false><<<a.n_tiles, kTileBlocks, 0, s>>>(*a.tmap, a.coef, a.imgs, a.tiles, a.qtabs, a.pixels, a.status);
+        k_idct_csc<false><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status);
 }
 
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s)

@@ -32,14 +32,18 @@ struct DecodeArgs
     // sizes
     uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len;
     bool use_tma;
+    uint32_t huff_variant;   // bit 0: 128-bit stream prefetch, bit 1: deferred coefficient store
 };
+
+// A contiguous group of images of a batch: the unit the two-stream pipeline works on.
+struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1; };
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
 size_t huff_smem_bytes(uint32_t max_lut_len);
-void launch_prepass(const DecodeArgs &a, cudaStream_t s);   // 3 kernels
-void launch_huffman(const DecodeArgs &a, cudaStream_t s);   // 1 kernel
-void launch_idct(const DecodeArgs &a, cudaStream_t s);      // 1 kernel
+void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
+void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
+void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s);      // 1 kernel
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s);
 
 } // namespace b2j

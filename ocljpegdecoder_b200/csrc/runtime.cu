@@ -85,8 +85,11 @@ struct b2j_ctx
 {
     int device;
     cudaStream_t stream;
+    cudaStream_t stream2;   // the IDCT/colour stage of part p runs here while part p+1 is entropy-decoded
+    int n_parts;
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled;
     bool use_tma;
+    int sm_count;
     Pool dev_pool{false};
     Pool pin_pool{true};
     std::mutex mu;
@@ -117,6 +120,8 @@ struct b2j_batch
     CUtensorMap tmap;
     DecodeArgs args;
     uint32_t n_segs_total;
+    std::vector<PartRange> parts;
+    std::vector<cudaEvent_t> ev_huff, ev_idct;   // per part: entropy decode done / pixels done
     bool uploaded;
 };
 
@@ -224,8 +229,16 @@ extern "C" int b2j_create(int device, b2j_ctx **out)
     }
     b2j_ctx *ctx = new b2j_ctx;
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->encode_tiled = nullptr;
     CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {
+        const char *pe = getenv("B2J_PARTS");
+        ctx->n_parts = pe ? atoi(pe) : 1;   // > 1 was measured slower on B200: the entropy decoder is one wave
+        if (ctx->n_parts < 1) ctx->n_parts = 1;
+        if (ctx->n_parts > 16) ctx->n_parts = 16;
+    }
     CU_TRY(init_constants());
     CU_TRY(configure_kernels(kLutMaxEntries));
     void *fn = nullptr;
@@ -248,6 +261,7 @@ extern "C" void b2j_destroy(b2j_ctx *ctx)
     ctx->dev_pool.drain();
     ctx->pin_pool.drain();
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -269,6 +283,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->uploaded = false;
 
     std::vector<uint32_t> chunk_img;
+    std::vector<uint32_t> img_cta0((size_t)n + 1), img_tile0((size_t)n + 1), img_chunk0((size_t)n + 1);
     std::vector<HuffCtaDev> ctas;
     std::vector<TileDev> tiles;
     std::vector<uint16_t> luts;
@@ -288,6 +303,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         if (d.width <= 0 || d.height <= 0 || d.mcu_count <= 0 || d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset ||
             d.scan_size >= 0xFFFF0000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
         { rc = B2J_E_ARG; break; }
+        img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
         im.raw_off = raw_total;
         im.raw_len = (uint32_t)d.scan_size;
         raw_total += align_up((size_t)im.raw_len + 32, 16);
@@ -314,7 +330,11 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         im.ny_blks = (uint32_t)d.blks_per_mcu[0];
         im.yh = (uint32_t)(d.sampling[0] >> 4);
         const uint32_t mcus_per_tile = kTileBlocks / im.tot_blks;
-        for (uint32_t m = 0; m < im.mcu_count; m += mcus_per_tile) tiles.push_back({(uint32_t)i, m});
+        for (uint32_t m = 0; m < im.mcu_count; m += mcus_per_tile)
+        {
+            const uint32_t n = im.mcu_count - m < mcus_per_tile ? im.mcu_count - m : mcus_per_tile;
+            tiles.push_back({(uint32_t)i, m, im.blk_first + m * im.tot_blks, im.mode | (n << 8)});
+        }
         // quantisers: file (zig-zag) order -> natural order, per component (decoder.cpp:315,340)
         for (int c = 0; c < 3; c++)
             for (int k = 0; k < 64; k++)
@@ -356,6 +376,29 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     }
     if (rc != B2J_OK) { delete b; return rc; }
     if (blk_total + kTileBlocks >= 0xFFFFFFF0ull) { delete b; return B2J_E_ARG; }
+    img_cta0[(size_t)n] = (uint32_t)ctas.size(); img_tile0[(size_t)n] = (uint32_t)tiles.size(); img_chunk0[(size_t)n] = (uint32_t)chunk_img.size();
+    {
+        // contiguous groups of images with similar block counts: the units of the two-stream pipeline
+        const int np = ctx->n_parts < n ? ctx->n_parts : n;
+        int i0 = 0;
+        for (int p = 0; p < np; p++)
+        {
+            int i1 = i0;
+            const size_t target = blk_total * (size_t)(p + 1) / (size_t)np;
+            while (i1 < n && (i1 == i0 || (size_t)b->imgs[(size_t)i1].blk_first + b->imgs[(size_t)i1].blk_count <= target) && n - i1 > np - p - 1) i1++;
+            if (p == np - 1) i1 = n;
+            b->parts.push_back({(uint32_t)i0, (uint32_t)i1, img_chunk0[(size_t)i0], img_chunk0[(size_t)i1], img_cta0[(size_t)i0], img_cta0[(size_t)i1],
+                                img_tile0[(size_t)i0], img_tile0[(size_t)i1]});
+            i0 = i1;
+        }
+        b->ev_huff.resize(b->parts.size());
+        b->ev_idct.resize(b->parts.size());
+        for (size_t p = 0; p < b->parts.size(); p++)
+        {
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_huff[p], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_idct[p], cudaEventDisableTiming));
+        }
+    }
 
     // ---- input blob layout
     size_t off = 0;
@@ -371,7 +414,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
 
     // ---- scratch layout
     off = 0;
-    b->off_clean = place(raw_total + 64);
+    b->off_clean = place(raw_total + 256);   // the bit readers prefetch up to 48 bytes past a segment
     b->off_chunk_cnt = place(4 * chunk_img.size());
     b->off_chunk_term = place(4 * chunk_img.size());
     b->off_chunk_bk = place(4 * chunk_img.size());
@@ -411,7 +454,9 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         const ImgDev &im = b->imgs[(size_t)i];
         uint8_t *dst = b->h_blob + b->off_raw + im.raw_off;
         memcpy(dst, files[i] + descs[i].scan_offset, im.raw_len);
-        memset(dst + im.raw_len, 0, align_up((size_t)im.raw_len + 32, 16) - im.raw_len);
+        // pad with FF D9 D9 ...: running off the end of a scan then looks like EOI to the pre-pass
+        memset(dst + im.raw_len, 0xD9, align_up((size_t)im.raw_len + 32, 16) - im.raw_len);
+        dst[im.raw_len] = 0xFF;
     }
 
     rc = make_tensor_map(ctx, b);
@@ -442,11 +487,15 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.n_tiles = (uint32_t)tiles.size();
     a.max_lut_len = max_lut_len;
     a.use_tma = ctx->use_tma;
+    {
+        const char *hv = getenv("B2J_HUFF_VARIANT");
+        a.huff_variant = hv ? (uint32_t)atoi(hv) : 0u;
+    }
 
     b2j_batch_info &inf = b->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_images = n;
-    inf.kernel_launches = 5;
+    inf.kernel_launches = 5 * (int32_t)b->parts.size();
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
     inf.scan_bytes = scan_bytes;
@@ -464,6 +513,9 @@ extern "C" void b2j_batch_destroy(b2j_batch *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(b->ctx->stream2);
+    for (auto &e : b->ev_huff) cudaEventDestroy(e);
+    for (auto &e : b->ev_idct) cudaEventDestroy(e);
     release_batch_buffers(b);
     delete b;
 }
@@ -491,21 +543,66 @@ extern "C" int b2j_batch_upload(b2j_batch *b, void *stream)
     return B2J_OK;
 }
 
-static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* 4 or NULL */)
+// Events of one timed step: [0] start, [1] end, then 5 per part: before pre-pass, after pre-pass, after
+// Huffman (stream 1), before IDCT, after IDCT (stream 2).
+static size_t events_per_step(const b2j_batch *b) { return 2 + 5 * b->parts.size(); }
+
+// One decode of the whole batch. The batch is split into parts; part p's IDCT/colour kernel runs on the
+// context's second stream while part p+1 is still in the pre-pass / entropy decoder on `s`: the two
+// stages stress different resources (shared-memory LUT gathers vs. ALU + HBM) and overlap well.
+// On return everything is ordered behind `s` again.
+static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* events_per_step() or NULL */)
 {
     if (!b->uploaded) { t_last_error = "b2j_batch_decode before b2j_batch_upload"; return B2J_E_ARG; }
     const DecodeArgs &a = b->args;
+    cudaStream_t s2 = b->ctx->stream2;
     if (ev) CU_TRY(cudaEventRecord(ev[0], s));
     CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
     CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
-    launch_prepass(a, s);
+    const size_t np = b->parts.size();
+    for (size_t p = 0; p < np; p++)
+    {
+        const PartRange &r = b->parts[p];
+        cudaEvent_t *pe = ev ? ev + 2 + 5 * p : nullptr;
+        if (pe) CU_TRY(cudaEventRecord(pe[0], s));
+        launch_prepass(a, r, s);
+        if (pe) CU_TRY(cudaEventRecord(pe[1], s));
+        launch_huffman(a, r, s);
+        if (pe) CU_TRY(cudaEventRecord(pe[2], s));
+        if (np == 1)
+        {
+            if (pe) CU_TRY(cudaEventRecord(pe[3], s));
+            launch_idct(a, r, s);
+            if (pe) CU_TRY(cudaEventRecord(pe[4], s));
+        }
+        else
+        {
+            CU_TRY(cudaEventRecord(b->ev_huff[p], s));
+            CU_TRY(cudaStreamWaitEvent(s2, b->ev_huff[p], 0));
+            if (pe) CU_TRY(cudaEventRecord(pe[3], s2));
+            launch_idct(a, r, s2);
+            if (pe) CU_TRY(cudaEventRecord(pe[4], s2));
+            CU_TRY(cudaEventRecord(b->ev_idct[p], s2));
+        }
+    }
+    if (np > 1) CU_TRY(cudaStreamWaitEvent(s, b->ev_idct[np - 1], 0));   // stream 2 is in order: the last part covers all
     if (ev) CU_TRY(cudaEventRecord(ev[1], s));
-    launch_huffman(a, s);
-    if (ev) CU_TRY(cudaEventRecord(ev[2], s));
-    launch_idct(a, s);
-    if (ev) CU_TRY(cudaEventRecord(ev[3], s));
     CU_TRY(cudaGetLastError());
     return B2J_OK;
+}
+
+static void collect_times(const b2j_batch *b, cudaEvent_t *ev, b2j_stage_times *t)
+{
+    t->prepass_ms = t->huffman_ms = t->idct_ms = 0.f;
+    for (size_t p = 0; p < b->parts.size(); p++)
+    {
+        cudaEvent_t *pe = ev + 2 + 5 * p;
+        float x = 0.f;
+        cudaEventElapsedTime(&x, pe[0], pe[1]); t->prepass_ms += x;
+        cudaEventElapsedTime(&x, pe[1], pe[2]); t->huffman_ms += x;
+        cudaEventElapsedTime(&x, pe[3], pe[4]); t->idct_ms += x;
+    }
+    cudaEventElapsedTime(&t->total_ms, ev[0], ev[1]);
 }
 
 extern "C" int b2j_batch_decode(b2j_batch *b, void *stream)
@@ -517,26 +614,7 @@ extern "C" int b2j_batch_decode(b2j_batch *b, void *stream)
 
 extern "C" int b2j_batch_decode_timed(b2j_batch *b, void *stream, b2j_stage_times *times)
 {
-    if (!b || !times) return B2J_E_ARG;
-    CU_TRY(cudaSetDevice(b->ctx->device));
-    cudaStream_t s = pick_stream(b, stream);
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; i++) CU_TRY(cudaEventCreate(&ev[i]));
-    int rc = enqueue_decode(b, s, ev);
-    if (rc == B2J_OK)
-    {
-        cudaError_t e = cudaEventSynchronize(ev[3]);
-        if (e != cudaSuccess) rc = fail_cuda(e, "cudaEventSynchronize");
-        else
-        {
-            cudaEventElapsedTime(&times->prepass_ms, ev[0], ev[1]);
-            cudaEventElapsedTime(&times->huffman_ms, ev[1], ev[2]);
-            cudaEventElapsedTime(&times->idct_ms, ev[2], ev[3]);
-            cudaEventElapsedTime(&times->total_ms, ev[0], ev[3]);
-        }
-    }
-    for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
-    return rc;
+    return b2j_batch_decode_steps(b, stream, 1, times, nullptr);
 }
 
 extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j_stage_times *per_step, float *total_ms)
@@ -544,10 +622,11 @@ extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j
     if (!b || steps <= 0) return B2J_E_ARG;
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t s = pick_stream(b, stream);
-    std::vector<cudaEvent_t> ev((size_t)steps * 4);
+    const size_t per = events_per_step(b);
+    std::vector<cudaEvent_t> ev((size_t)steps * per);
     for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
     int rc = B2J_OK;
-    for (int k = 0; k < steps && rc == B2J_OK; k++) rc = enqueue_decode(b, s, &ev[(size_t)k * 4]);
+    for (int k = 0; k < steps && rc == B2J_OK; k++) rc = enqueue_decode(b, s, &ev[(size_t)k * per]);
     if (rc == B2J_OK)
     {
         cudaError_t e = cudaStreamSynchronize(s);
@@ -555,15 +634,8 @@ extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j
     }
     if (rc == B2J_OK)
     {
-        for (int k = 0; k < steps && per_step; k++)
-        {
-            cudaEvent_t *v = &ev[(size_t)k * 4];
-            cudaEventElapsedTime(&per_step[k].prepass_ms, v[0], v[1]);
-            cudaEventElapsedTime(&per_step[k].huffman_ms, v[1], v[2]);
-            cudaEventElapsedTime(&per_step[k].idct_ms, v[2], v[3]);
-            cudaEventElapsedTime(&per_step[k].total_ms, v[0], v[3]);
-        }
-        if (total_ms) cudaEventElapsedTime(total_ms, ev[0], ev[(size_t)steps * 4 - 1]);
+        for (int k = 0; k < steps && per_step; k++) collect_times(b, &ev[(size_t)k * per], &per_step[k]);
+        if (total_ms) cudaEventElapsedTime(total_ms, ev[0], ev[(size_t)(steps - 1) * per + 1]);
     }
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;

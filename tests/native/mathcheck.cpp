@@ -40,19 +40,22 @@ long chk_csc_exhaustive(int32_t first_bad[3])
 }
 
 // Builds the two-level LUT of one table and decodes `peek` (32 bits, MSB first) with it, the way
-// lut_lookup() in kernels.cu does. Returns the leaf entry (0 = no codeword), -1 on build failure.
+// lut_lookup() in kernels.cu does. Returns len | size<<8 | run<<16 (0 = no codeword), -1 on build failure.
 int chk_lut_decode(const uint8_t counts[16], const uint8_t *symbols, int is_dc, uint32_t peek, int *n_entries)
 {
     std::vector<uint16_t> t;
     if (!b2j::build_huff_lut(counts, symbols, is_dc != 0, t, b2j::kLutMaxEntries)) return -1;
     if (n_entries) *n_entries = (int)t.size();
     uint32_t e = t[peek >> (32 - b2j::kLutBits)];
-    if (e & b2j::kLutEscape)
+    if ((e & 63u) < 32u)
     {
-        const uint32_t nb = e & 15u, off = (e >> 4) & 0x7FFu;
+        if (e == 0) return 0;
+        const uint32_t nb = e & 63u, off = e >> 6;
         e = t[(1u << b2j::kLutBits) + off + ((peek << b2j::kLutBits) >> (32u - nb))];
+        if (e == 0) return 0;
     }
-    return (int)e;
+    const int len = (int)(e & 63u) - 32, size = 32 - (int)((e >> 6) & 63u), run = (int)(e >> 12);
+    return len | (size << 8) | (run << 16);
 }
 
 int chk_zigzag(int i)

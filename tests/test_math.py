@@ -90,7 +90,7 @@ def _check_table(chk, bits, vals, is_dc):
             peek = ((code << (32 - l)) | tail) & 0xFFFFFFFF
             e = chk.chk_lut_decode(bytes(bits), bytes(vals), is_dc, peek, ctypes.byref(n))
             assert e > 0
-            ln, size, run = e & 31, (e >> 5) & 31, (e >> 10) & 15
+            ln, size, run = e & 0xFF, (e >> 8) & 0xFF, (e >> 16) & 0xFF
             assert ln == l
             if is_dc:
                 assert size == sym and run == 0
