@@ -63,7 +63,7 @@ class StageTimes(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libb2j.so")
+    return os.environ.get("B2J_LIBRARY") or os.path.join(_HERE, "lib", "libb2j.so")
 
 
 _LIB = None

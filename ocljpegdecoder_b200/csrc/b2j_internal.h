@@ -11,8 +11,9 @@
 namespace b2j {
 
 // ---------------------------------------------------------------- constants ------------
-constexpr int kScanChunkBytes = 4096;    // bytes of raw scan one CTA of the pre-pass handles
-constexpr int kScanThreads = 256;        // 16 bytes per thread
+constexpr int kScanGroups = 4;           // 16-byte groups per thread in the pre-pass (4 loads in flight per thread)
+constexpr int kScanThreads = 256;
+constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of raw scan one CTA of the pre-pass handles
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
 constexpr int kLutBits = 10;             // primary Huffman LUT width
 constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set

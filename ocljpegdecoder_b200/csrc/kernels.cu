@@ -76,17 +76,12 @@ __device__ __forceinline__ uint32_t squeeze(const uint32_t f[4]) { return (f[0] 
 __device__ __forceinline__ bool flag_at(const uint32_t f[4], int j) { return (f[j >> 2] >> (8 * (j & 3) + 7)) & 1u; }
 
 // The host pads every image's scan with FF D9 D9 ..., so running off the end looks like EOI and no
-// end-of-data special case is needed: the pad FF is a terminator and everything behind it is cut.
-__device__ __forceinline__ ScanFlags classify16(const uint8_t *__restrict__ scan, uint32_t raw_len, uint32_t pos, uint32_t w[4])
+// end-of-data special case is needed: the pad FF is a terminator and everything behind it is cut
+// (bytes behind it, possibly the next image's, are classified too but never used).
+// w: the 16 bytes; prev / next: the byte before / after them.
+__device__ __forceinline__ ScanFlags classify16(const uint32_t w[4], uint32_t prev, uint32_t next)
 {
     ScanFlags f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) f.keep[i] = f.mark[i] = f.term[i] = 0u;
-    if (pos > raw_len) { w[0] = w[1] = w[2] = w[3] = 0; return f; }
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(scan + pos));   // scan base and pos are 16 B aligned
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    const uint32_t prev = pos ? (uint32_t)__ldg(scan + pos - 1) : 0u;      // byte before the thread's 16
-    const uint32_t next = (uint32_t)__ldg(scan + pos + 16);                // byte after (pad bytes exist)
     uint32_t F[6], Z[5], D[5];   // index i+1 = word i; F[0] = predecessor, [5] = successor
     F[0] = prev == 0xFFu ? 0x80000000u : 0u;
 #pragma unroll
@@ -114,32 +109,66 @@ __device__ __forceinline__ ScanFlags classify16(const uint8_t *__restrict__ scan
     return f;
 }
 
+// A thread's kScanGroups x 16 consecutive bytes of the chunk, loaded with all vector loads in flight
+// at once, and their classification. pos = offset of the thread's first byte in the image's scan.
+struct ScanThread
+{
+    uint32_t w[kScanGroups][4];
+    ScanFlags f[kScanGroups];
+
+    __device__ __forceinline__ void load_classify(const uint8_t *__restrict__ scan, uint32_t pos)
+    {
+        uint4 v[kScanGroups];
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++) v[g] = __ldg(reinterpret_cast<const uint4 *>(scan + pos) + g);   // 16 B aligned
+        const uint32_t prev = pos ? (uint32_t)__ldg(scan + pos - 1) : 0u;
+        const uint32_t next = (uint32_t)__ldg(scan + pos + 16 * kScanGroups);                                 // pad bytes exist
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++) { w[g][0] = v[g].x; w[g][1] = v[g].y; w[g][2] = v[g].z; w[g][3] = v[g].w; }
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++)
+            f[g] = classify16(w[g], g ? (w[g - 1][3] >> 24) : prev, g + 1 < kScanGroups ? (w[g + 1][0] & 0xFFu) : next);
+    }
+    // thread-local position (0 .. 16*kScanGroups-1) of the first terminator, or kNoTerm
+    __device__ __forceinline__ uint32_t first_term() const
+    {
+        uint32_t best = kNoTerm;
+#pragma unroll
+        for (int g = kScanGroups - 1; g >= 0; g--)
+#pragma unroll
+            for (int i = 3; i >= 0; i--)
+                if (f[g].term[i]) best = 16u * g + 4u * i + ((uint32_t)(__ffs(f[g].term[i]) - 1) >> 3);
+        return best;
+    }
+    // drops the flags of bytes at or behind thread-local position `limit`
+    __device__ __forceinline__ void cut(uint32_t limit)
+    {
+        if (limit >= 16u * kScanGroups) return;
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++)
+        {
+            uint32_t m[4];
+            first_n_flags(limit > 16u * g ? (int)min(limit - 16u * g, 16u) : 0, m);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { f[g].keep[i] &= m[i]; f[g].mark[i] &= m[i]; }
+        }
+    }
+};
+
 // Chunk-local position of the first terminator, or kNoTerm.
-__device__ __forceinline__ uint32_t block_first_term(const uint32_t term[4], uint32_t tid, uint32_t *s_min)
+__device__ __forceinline__ uint32_t block_first_term(uint32_t local_term, uint32_t tid, uint32_t *s_min)
 {
     if (tid == 0) *s_min = kNoTerm;
     __syncthreads();
-    if (term[0] | term[1] | term[2] | term[3])
-    {
-        uint32_t j = 0;
-        if (term[0]) j = (uint32_t)(__ffs(term[0]) - 1) >> 3;
-        else if (term[1]) j = 4u + ((uint32_t)(__ffs(term[1]) - 1) >> 3);
-        else if (term[2]) j = 8u + ((uint32_t)(__ffs(term[2]) - 1) >> 3);
-        else j = 12u + ((uint32_t)(__ffs(term[3]) - 1) >> 3);
-        atomicMin(s_min, tid * 16u + j);
-    }
+    if (local_term != kNoTerm) atomicMin(s_min, tid * (16u * kScanGroups) + local_term);
     __syncthreads();
     return *s_min;
 }
 
-// Drops the flags of bytes at or behind the chunk-local terminator position.
-__device__ __forceinline__ void cut_at(uint32_t term_pos, uint32_t tid, uint32_t keep[4], uint32_t mark[4])
+__device__ __forceinline__ uint32_t local_limit(uint32_t chunk_term, uint32_t tid)
 {
-    if (term_pos >= tid * 16u + 16u) return;
-    uint32_t m[4];
-    first_n_flags(term_pos > tid * 16u ? (int)(term_pos - tid * 16u) : 0, m);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { keep[i] &= m[i]; mark[i] &= m[i]; }
+    const uint32_t lo = tid * (16u * kScanGroups);
+    return chunk_term <= lo ? 0u : chunk_term - lo;   // kNoTerm and anything behind the thread's bytes: no cut
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -150,12 +179,14 @@ k_scan_count(const uint8_t *__restrict__ raw, const ImgDev *__restrict__ imgs, c
     __shared__ uint32_t s_warp[kScanThreads / 32];
     const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x;
     const ImgDev &im = imgs[chunk_img[c]];
-    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * 16u;
-    uint32_t w[4];
-    ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, w);
-    const uint32_t term = block_first_term(f.term, tid, &s_min);
-    cut_at(term, tid, f.keep, f.mark);
-    uint32_t packed = __popc(squeeze(f.keep)) | (__popc(squeeze(f.mark)) << 16);
+    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * (16u * kScanGroups);
+    ScanThread st;
+    st.load_classify(raw + im.raw_off, pos);
+    const uint32_t term = block_first_term(st.first_term(), tid, &s_min);
+    st.cut(local_limit(term, tid));
+    uint32_t packed = 0;
+#pragma unroll
+    for (int g = 0; g < kScanGroups; g++) packed += __popc(squeeze(st.f[g].keep)) | (__popc(squeeze(st.f[g].mark)) << 16);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
     if ((tid & 31) == 0) s_warp[tid >> 5] = packed;
@@ -219,9 +250,82 @@ k_scan_chunks(const ImgDev *__restrict__ imgs, int img0, int img1, const uint32_
     }
 }
 
+// The thread's kept bytes of one 16-byte group -> shared memory at s_out[o ...]. B: the group's bytes.
+// Rare path first (a byte is stuffing, fill, a marker or behind the end of the scan): record restart
+// interval starts, squeeze dropped bytes out of the register array. Then single bytes up to the next
+// word boundary, whole words, tail bytes.
+__device__ __forceinline__ void write_group(uint8_t *__restrict__ s_out, uint32_t o, const uint32_t w[4], const ScanFlags &f,
+                                            uint32_t nkeep, uint32_t &rank, uint32_t clean_pos, const ImgDev &im, uint32_t img_idx,
+                                            uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
+{
+    uint32_t B[4] = {w[0], w[1], w[2], w[3]};
+    const uint32_t any_mark = f.mark[0] | f.mark[1] | f.mark[2] | f.mark[3];
+    if (nkeep != 16u || any_mark)
+    {
+        uint32_t keep16 = 0, mark16 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            keep16 |= ((((f.keep[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+            mark16 |= ((((f.mark[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+        }
+        while (mark16)
+        {
+            const uint32_t j = (uint32_t)__ffs(mark16) - 1u;
+            mark16 &= mark16 - 1u;
+            if (im.has_dri && rank + 1 < im.n_segs)
+            {
+                seg_start[im.seg_first + rank + 1] = clean_pos + __popc(keep16 & ((1u << j) - 1u));
+                const uint32_t wj = j < 4u ? w[0] : (j < 8u ? w[1] : (j < 12u ? w[2] : w[3]));
+                const uint32_t bj = (wj >> (8 * (j & 3u))) & 0xFFu;
+                if (bj != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
+            }
+            rank++;
+        }
+        // squeeze the dropped bytes out, highest first (bytes above the last kept one need no move)
+        const uint32_t span = keep16 ? 32u - (uint32_t)__clz(keep16) : 0u;
+        uint32_t drop = ~keep16 & ((1u << span) - 1u);
+        while (drop)
+        {
+            const uint32_t j = 31u - (uint32_t)__clz(drop);
+            drop ^= 1u << j;
+            const uint32_t wi = j >> 2, lm = (1u << (8u * (j & 3u))) - 1u;
+            const uint32_t sh0 = __funnelshift_r(B[0], B[1], 8), sh1 = __funnelshift_r(B[1], B[2], 8),
+                           sh2 = __funnelshift_r(B[2], B[3], 8), sh3 = B[3] >> 8;
+            B[0] = wi == 0u ? ((B[0] & lm) | (sh0 & ~lm)) : B[0];
+            B[1] = wi == 1u ? ((B[1] & lm) | (sh1 & ~lm)) : (wi < 1u ? sh1 : B[1]);
+            B[2] = wi == 2u ? ((B[2] & lm) | (sh2 & ~lm)) : (wi < 2u ? sh2 : B[2]);
+            B[3] = wi == 3u ? ((B[3] & lm) | (sh3 & ~lm)) : sh3;
+        }
+    }
+    uint32_t n = nkeep;
+    const uint32_t head = min((4u - (o & 3u)) & 3u, n);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if ((uint32_t)k < head) s_out[o + k] = (uint8_t)(B[0] >> (8 * k));
+    if (head)
+    {
+        const uint32_t hs = head * 8u;   // drop the head bytes from the register array
+        B[0] = __funnelshift_r(B[0], B[1], hs);
+        B[1] = __funnelshift_r(B[1], B[2], hs);
+        B[2] = __funnelshift_r(B[2], B[3], hs);
+        B[3] = B[3] >> hs;
+    }
+    o += head; n -= head;
+    uint32_t *wo = reinterpret_cast<uint32_t *>(s_out + o);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if ((uint32_t)(4 * k + 4) <= n) wo[k] = B[k];
+    const uint32_t full = n >> 2, tail = n & 3u;
+    const uint32_t tw = full == 0u ? B[0] : (full == 1u ? B[1] : (full == 2u ? B[2] : B[3]));
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if ((uint32_t)k < tail) s_out[o + full * 4u + k] = (uint8_t)(tw >> (8 * k));
+}
+
 // Writes the clean stream of one chunk: the kept bytes are compacted in shared memory (at an offset
 // congruent to their global address mod 16) and then copied out with 128-bit stores.
-__global__ void __launch_bounds__(kScanThreads, 4)
+__global__ void __launch_bounds__(kScanThreads, 3)
 k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
                 const uint32_t *__restrict__ chunk_img, const uint32_t *__restrict__ chunk_term,
                 const uint32_t *__restrict__ chunk_base_keep, const uint32_t *__restrict__ chunk_base_mark,
@@ -234,13 +338,17 @@ k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, co
     if (base_keep == kChunkDead) return;   // behind the end of the scan (uniform for the CTA)
     const uint32_t img_idx = chunk_img[c];
     const ImgDev &im = imgs[img_idx];
-    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * 16u;
-    uint32_t w[4];
-    ScanFlags f = classify16(raw + im.raw_off, im.raw_len, pos, w);
-    cut_at(chunk_term[c], tid, f.keep, f.mark);
-    const uint32_t nkeep = __popc(squeeze(f.keep));
-    const uint32_t any_mark = f.mark[0] | f.mark[1] | f.mark[2] | f.mark[3];
-    const uint32_t mine = nkeep | (__popc(squeeze(f.mark)) << 16);
+    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * (16u * kScanGroups);
+    ScanThread st;
+    st.load_classify(raw + im.raw_off, pos);
+    st.cut(local_limit(chunk_term[c], tid));
+    uint32_t nkeep[kScanGroups], mine = 0;
+#pragma unroll
+    for (int g = 0; g < kScanGroups; g++)
+    {
+        nkeep[g] = __popc(squeeze(st.f[g].keep));
+        mine += nkeep[g] | (__popc(squeeze(st.f[g].mark)) << 16);
+    }
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -263,38 +371,12 @@ k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, co
     const uint64_t g0 = im.raw_off + base_keep;                      // where they go in clean[]
     const uint32_t a = (uint32_t)(g0 & 15u);
     uint32_t lo = excl & 0xFFFFu;                                    // chunk-local output offset of this thread
-    if (nkeep == 16u)
+    uint32_t rank = chunk_base_mark[c] + (excl >> 16);               // ordinal of the next RSTn in the image
+#pragma unroll
+    for (int g = 0; g < kScanGroups; g++)
     {
-        uint8_t *d = s_out + a + lo;
-        if (((a + lo) & 3u) == 0u)
-        {
-#pragma unroll
-            for (int i = 0; i < 4; i++) reinterpret_cast<uint32_t *>(d)[i] = w[i];
-        }
-        else
-        {
-#pragma unroll
-            for (int j = 0; j < 16; j++) d[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
-        }
-    }
-    else if (nkeep | any_mark)
-    {
-        uint32_t rank = chunk_base_mark[c] + (excl >> 16);           // ordinal of the next RSTn in the image
-#pragma unroll
-        for (int j = 0; j < 16; j++)
-        {
-            const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (flag_at(f.mark, j))
-            {
-                if (im.has_dri && rank + 1 < im.n_segs)
-                {
-                    seg_start[im.seg_first + rank + 1] = base_keep + lo;
-                    if (b != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
-                }
-                rank++;
-            }
-            if (flag_at(f.keep, j)) s_out[a + lo++] = (uint8_t)b;
-        }
+        write_group(s_out, a + lo, st.w[g], st.f[g], nkeep[g], rank, base_keep + lo, im, img_idx, seg_start, status);
+        lo += nkeep[g];
     }
     __syncthreads();
     // copy out: 16-byte vectors where whole, single bytes at the two ragged ends
@@ -899,8 +981,11 @@ __device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMo
 // Measured on B200 (profiles/): a persistent double-buffered variant and a warp-autonomous variant of
 // this kernel were both slower -- the kernel is bound by dependent-issue latency at 24 warps per SM,
 // not by the latency in front of a tile, so the simplest structure wins.
+#ifndef B2J_IDCT_MIN_CTAS
+#define B2J_IDCT_MIN_CTAS 5   // measured on B200: 64 registers with ~220 B of spills beats 80 registers at 4 CTAs per SM
+#endif
 template <bool USE_TMA>
-__global__ void __launch_bounds__(kTileBlocks, 4)
+__global__ void __launch_bounds__(kTileBlocks, B2J_IDCT_MIN_CTAS)
 k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
            const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
 {

@@ -409,7 +409,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_tiles = place(sizeof(TileDev) * tiles.size());
     b->off_luts = place(sizeof(uint16_t) * luts.size());
     b->off_qtabs = place(sizeof(uint16_t) * qtabs.size());
-    b->off_raw = place(raw_total + 64);
+    b->off_raw = place(raw_total + kScanChunkBytes + 64);   // the pre-pass reads whole chunks
     b->blob_bytes = off;
 
     // ---- scratch layout
