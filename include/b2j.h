@@ -166,6 +166,11 @@ int b2j_batch_sync(b2j_batch *batch, void *stream);
 /* Per-image status words (B2J_ST_* bits). Synchronises the stream. */
 int b2j_batch_status(b2j_batch *batch, void *stream, int32_t *status /* n */);
 
+/* Convergence evidence of the self-synchronising entropy decoder (streams without DRI) for the most
+ * recent decode: out8[r] = sub-sequence exit states that round r (1..) still changed, out8[7] =
+ * sub-sequences the sequential sweep had to re-walk. Synchronises. */
+int b2j_batch_sync_stats(b2j_batch *batch, void *stream, uint32_t *out8);
+
 /* Device-resident results. Pixels: BGRA (A = 0), top-down, tight pitch width*4. */
 int b2j_batch_pixels_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes);
 /* Coefficient plane: int16[blk_count][64], natural order, QUANTISED (dequantisation happens

@@ -16,7 +16,7 @@ B2J_E_NODEVICE = -7
 EXPORTED_SYMBOLS = [
     "b2j_abi_version", "b2j_strerror", "b2j_last_error", "b2j_parse_header", "b2j_device_count",
     "b2j_create", "b2j_destroy", "b2j_batch_create", "b2j_batch_destroy", "b2j_batch_get_info",
-    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status",
+    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status", "b2j_batch_sync_stats",
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
     "b2j_batch_read_coefs", "b2j_decode_host",
 ]
@@ -99,6 +99,7 @@ def load_library():
     L.b2j_batch_decode_steps.argtypes = [vp, vp, ci, ctypes.POINTER(StageTimes), ctypes.POINTER(ctypes.c_float)]
     L.b2j_batch_sync.argtypes = [vp, vp]
     L.b2j_batch_status.argtypes = [vp, vp, vp]
+    L.b2j_batch_sync_stats.argtypes = [vp, vp, vp]
     L.b2j_batch_pixels_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.b2j_batch_coefs_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.b2j_batch_read_pixels.argtypes = [vp, vp, ci, vp]
@@ -223,6 +224,11 @@ class Batch:
         st = np.zeros(self.n, np.int32)
         _check(self.lib.b2j_batch_status(self._h, stream, st.ctypes.data), "b2j_batch_status")
         return st
+
+    def sync_stats(self, stream=None):
+        out = np.zeros(8, np.uint32)
+        _check(self.lib.b2j_batch_sync_stats(self._h, stream, out.ctypes.data), "b2j_batch_sync_stats")
+        return out
 
     def pixels(self, i, stream=None):
         d = self.descs[i]

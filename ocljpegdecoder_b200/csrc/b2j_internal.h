@@ -15,6 +15,8 @@ constexpr int kScanGroups = 4;           // 16-byte groups per thread in the pre
 constexpr int kScanThreads = 256;
 constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of raw scan one CTA of the pre-pass handles
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
+constexpr int kSubBytes = 128;           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
+constexpr int kSyncRounds = 6;           // parallel synchronisation rounds before the sequential sweep
 constexpr int kLutBits = 10;             // primary Huffman LUT width
 constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set
 constexpr int kLutMaxEntries = 12288;    // u16 entries of one LUT set (24 KB of shared memory)
@@ -59,7 +61,25 @@ struct ImgDev
     uint32_t ny_blks;      // luma blocks per MCU
     uint32_t yh;           // luma blocks per MCU row
     uint32_t wide_q;       // 1 when some quantiser value exceeds 255
+    uint32_t sub_first;    // self-synchronising path (streams without DRI): first sub-sequence record of this image
+    uint32_t n_sub_max;    // upper bound of its sub-sequence count (from raw_len); 0 = restart-interval path
 };
+
+// Self-synchronising decode, one record per sub-sequence j of kSubBytes*8 bits of clean stream:
+// the decoder state when it leaves the sub-sequence (the first symbol that STARTS at or behind the
+// end of the sub-sequence is not decoded), and what was met inside it.
+struct SubRec
+{
+    uint32_t p;         // bit position of the exit state (>= end of the sub-sequence)
+    uint32_t cz;        // block-in-MCU index | zig-zag position << 8 (0 = next symbol is a DC code); kSubInvalid = no valid state
+    uint32_t nblk;      // blocks whose DC code starts inside the sub-sequence
+    int32_t dc[3];      // sum of the DC differences of those blocks, per component
+    uint32_t fs;        // bit position of the first of those blocks (kSubNone: none)
+    uint32_t fc;        // its block-in-MCU index
+};
+struct SubPre { uint32_t blk; int32_t dc[3]; };   // exclusive prefix over the sub-sequences of one image
+constexpr uint32_t kSubInvalid = 0xFFFFFFFFu;
+constexpr uint32_t kSubNone = 0xFFFFFFFFu;
 
 struct HuffCtaDev { uint32_t img; uint32_t seg_first; };   // segment index local to the image
 // One IDCT/colour tile: up to kTileBlocks consecutive blocks (whole MCUs) of one image.

@@ -487,11 +487,17 @@ __device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
     return (int32_t)((mag ^ ~pos) - ~pos);                      // negate when negative
 }
 
-template <bool WIDE, bool DEFER>
+// SYNC = false: a lane is a restart interval (byte-aligned start from seg_start[], DC predictors 0, the
+//   block-in-MCU phase is 0 and therefore uniform across the warp).
+// SYNC = true : a lane is a sub-sequence of a stream without restart markers; its first block, bit
+//   position, MCU phase, block index and DC predictors come from the self-synchronisation passes
+//   (SubRec / SubPre), and the table choice is per lane.
+template <bool WIDE, bool DEFER, bool SYNC>
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
               const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ clean_len,
-              const uint16_t *__restrict__ luts, int16_t *__restrict__ coef, int32_t *__restrict__ status)
+              const uint16_t *__restrict__ luts, int16_t *__restrict__ coef, int32_t *__restrict__ status,
+              const SubRec *__restrict__ recs, const SubPre *__restrict__ pres)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // [ per-lane block slots: kHuffThreads * 128 B ][ zig-zag byte offsets: 64 B ][ LUT set ]
@@ -516,29 +522,55 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 
     const uint32_t tot = im.tot_blks, ny = im.ny_blks;
     const uint32_t seg = cta.seg_first + tid;
-    bool active = seg < im.n_segs;
-    uint32_t start = 0, end = 0, nblk = 0, blk0 = 0;
-    bool check_end = false;
-    if (active)
+    uint32_t start = 0, end = 0, nblk = 0, blk0 = 0, start_bit = 0, bi = 0;
+    int32_t dc0 = 0, dc1 = 0, dc2 = 0;
+    int32_t err = 0;
+    bool check_end = false, active, decodable;
+    if (!SYNC)
     {
-        start = seg_start[im.seg_first + seg];
-        const uint32_t mcu0 = seg * im.restart_interval;
-        const uint32_t nmcu = min(im.restart_interval, im.mcu_count - mcu0);
-        nblk = nmcu * tot;
-        blk0 = im.blk_first + mcu0 * tot;
-        if (seg + 1 < im.n_segs) { end = seg_start[im.seg_first + seg + 1]; check_end = (end != kSegInvalid); }
-        if (!check_end) end = clean_len[cta.img];
+        active = seg < im.n_segs;
+        if (active)
+        {
+            start = seg_start[im.seg_first + seg];
+            const uint32_t mcu0 = seg * im.restart_interval;
+            const uint32_t nmcu = min(im.restart_interval, im.mcu_count - mcu0);
+            nblk = nmcu * tot;
+            blk0 = im.blk_first + mcu0 * tot;
+            if (seg + 1 < im.n_segs) { end = seg_start[im.seg_first + seg + 1]; check_end = (end != kSegInvalid); }
+            if (!check_end) end = clean_len[cta.img];
+        }
+        // a lane whose start is unknown (missing RSTn) still emits zero blocks so the plane is defined
+        decodable = active && start != kSegInvalid;
     }
-    // a lane whose start is unknown (missing RSTn) still emits zero blocks so the plane is defined
-    const bool decodable = active && start != kSegInvalid;
+    else
+    {
+        const uint32_t bits = clean_len[cta.img] * 8u;
+        const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+        active = seg < n_sub;
+        if (active)
+        {
+            const SubRec rec = recs[im.sub_first + seg];
+            const SubPre pre = pres[im.sub_first + seg];
+            if (rec.fs != kSubNone && pre.blk < im.blk_count)
+            {
+                nblk = min(rec.nblk, im.blk_count - pre.blk);           // bits behind the last block decode to junk blocks: dropped
+                blk0 = im.blk_first + pre.blk;
+                start_bit = rec.fs;
+                bi = rec.fc;
+                dc0 = pre.dc[0]; dc1 = pre.dc[1]; dc2 = pre.dc[2];
+            }
+            if (seg + 1 == n_sub && pre.blk + rec.nblk < im.blk_count) err |= B2J_ST_OVERRUN;   // the stream ends before the last block
+            end = clean_len[cta.img];
+        }
+        start = start_bit >> 3;
+        decodable = active && nblk > 0;
+    }
 
     BitReader<WIDE ? 2 : 1> br;
     const uint8_t *base = clean + im.raw_off;
     br.init(base + (decodable ? start : 0u));
-    const uint32_t bit0 = br.bitpos;
-
-    int32_t dc0 = 0, dc1 = 0, dc2 = 0;
-    int32_t err = 0;
+    const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
+    if (SYNC) br.bitpos += start_bit & 7u;
     bool dead = !decodable;
 
     uint32_t sm_base;   // kept opaque: otherwise the shared-window base is re-derived (S2R) inside the decode loop
@@ -550,7 +582,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     const uint32_t slot_key = sm_base + tid * 128u + ((lane & 7u) << 4);
 
     const uint32_t max_nblk = __reduce_max_sync(0xFFFFFFFFu, nblk);
-    uint32_t bi = 0;   // block index inside the MCU (uniform across the warp: segments start on MCU boundaries)
+    // bi: block index inside the MCU (!SYNC: uniform across the warp, segments start on MCU boundaries)
     for (uint32_t b = 0; b < max_nblk; b++)
     {
         const uint32_t comp = bi < ny ? 0u : (bi - ny + 1u);
@@ -647,9 +679,266 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         const uint64_t used = (bits + 7u) >> 3;
         const uint64_t avail = (uint64_t)end - start;
         if (used > avail) err |= B2J_ST_OVERRUN;
-        else if (check_end && used != avail) err |= B2J_ST_SEGMENT_END;
+        else if (!SYNC && check_end && used != avail) err |= B2J_ST_SEGMENT_END;
     }
     if (err) atomicOr(&status[cta.img], err);
+}
+
+// =====================================================================================
+// Self-synchronising entropy decode for streams without restart markers (north_star (1)).
+//
+// The clean stream of an image is cut into sub-sequences of kSubBytes*8 bits, one lane each. A JPEG
+// decoder state is (bit position, block index inside the MCU, zig-zag position); Huffman codes
+// self-synchronise, so a lane that starts from a GUESSED state at its sub-sequence border usually
+// falls into step with the true decoder within a few dozen symbols. Passes:
+//   round 0      every lane walks its own sub-sequence from the guess (border, block 0, DC expected)
+//                and records its exit state;
+//   round r >= 1 lane j walks sub-sequence j+1 from the recorded exit state of j and replaces the
+//                record of j+1 (exit state AND the block count / DC sums / first block start seen
+//                on the way). Round 1 does this for all j, later rounds only where the input state
+//                changed in the previous round. Record 0 starts from the true state, so record k is
+//                true after at most k rounds -- in practice after one or two;
+//   sweep        one warp per image runs over the records once more, in order, and repairs whatever
+//                the last parallel round still changed: correctness does not depend on luck;
+//   scan         exclusive prefix of block counts and DC sums -> first block index and DC predictors;
+//   decode       k_huff_decode<SYNC>: every lane decodes the blocks that START in its sub-sequence.
+struct WalkState { uint32_t p, c, z; };
+
+struct WalkResult
+{
+    uint32_t p, cz, nblk, fs, fc;
+    int32_t dc0, dc1, dc2;
+};
+
+// Walks the stream from state `s` while the next symbol starts before bit `limit`. No output.
+__device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict__ base, uint32_t sm_lut, const uint16_t *__restrict__ s_lut,
+                                                       WalkState s, uint32_t limit, uint32_t tot, uint32_t ny)
+{
+    WalkResult r;
+    r.nblk = 0; r.fs = kSubNone; r.fc = 0; r.dc0 = r.dc1 = r.dc2 = 0;
+    uint32_t p = s.p, c = s.c, z = s.z;
+    bool bad = false;
+    if (p < limit)
+    {
+        BitReader<1> br;
+        br.init(base + (p >> 3));
+        const uint32_t bit0 = br.bitpos;
+        br.bitpos += p & 7u;
+        const uint32_t p_byte = p & ~7u;
+        uint32_t comp = c < ny ? 0u : (c - ny + 1u);
+        uint32_t tab = sm_lut + 2u * (uint32_t)s_lut[(z == 0u ? 0u : 3u) + comp];
+        while (p < limit)
+        {
+            const uint32_t pk = br.peek();
+            uint32_t e = lut_first(tab, pk);
+            if (!(e & 32u))
+            {
+                e = lut_second(tab, pk, e);
+                if (!(e & 32u)) { bad = true; break; }
+            }
+            const uint32_t lenx = e & 63u, rs = e >> 6, s32 = rs & 63u;
+            if (z == 0u)
+            {
+                // DC code: a block starts here
+                if (r.fs == kSubNone) { r.fs = p; r.fc = c; }
+                r.nblk++;
+                const int32_t diff = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
+                if (comp == 0u) r.dc0 += diff; else if (comp == 1u) r.dc1 += diff; else r.dc2 += diff;
+                z = 1u;
+                tab = sm_lut + 2u * (uint32_t)s_lut[3u + comp];
+            }
+            else if (rs == 32u) z = 64u;      // EOB
+            else z += (e >> 12) + 1u;         // zero run + the coefficient (or the extra zero of a size-0 run)
+            br.bitpos += lenx - s32;
+            br.refill();
+            p = p_byte + br.nref * 32u + br.bitpos - bit0;
+            if (z >= 64u)
+            {
+                z = 0u;
+                c = (c + 1u == tot) ? 0u : c + 1u;
+                comp = c < ny ? 0u : (c - ny + 1u);
+                tab = sm_lut + 2u * (uint32_t)s_lut[comp];
+            }
+        }
+    }
+    // A non-code can only be met by a walk that started from a wrong guess (or in a corrupt stream, which
+    // the final decode flags): hand the next lane the same guess a first-round walk would use instead
+    // of a dead state, so that a wrong guess never poisons the records downstream.
+    r.p = bad ? max(p, limit) : p;
+    r.cz = bad ? 0u : (c | (z << 8));
+    return r;
+}
+
+__device__ __forceinline__ void store_rec(SubRec *__restrict__ dst, const WalkResult &r)
+{
+    uint4 a, b;
+    a.x = r.p; a.y = r.cz; a.z = r.nblk; a.w = (uint32_t)r.dc0;
+    b.x = (uint32_t)r.dc1; b.y = (uint32_t)r.dc2; b.z = r.fs; b.w = r.fc;
+    reinterpret_cast<uint4 *>(dst)[0] = a;
+    reinterpret_cast<uint4 *>(dst)[1] = b;
+}
+
+// round 0: lane j walks sub-sequence j from the guessed state. round >= 1: lane j walks sub-sequence j+1
+// from the exit state recorded for j (all lanes in round 1, afterwards only where that state changed
+// in the previous round).
+__global__ void __launch_bounds__(kHuffThreads)
+k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
+            const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
+            uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ stats)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
+    const uint32_t tid = threadIdx.x;
+    const HuffCtaDev cta = ctas[blockIdx.x];
+    const ImgDev &im = imgs[cta.img];
+    const uint32_t bits = clean_len[cta.img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    if (cta.seg_first >= n_sub) return;   // uniform: the clean stream is shorter than the raw bound
+    if (round > 1u && stats[round - 1u] == 0u) return;   // already converged (uniform for the whole grid)
+    if (round > 1u)
+    {
+        // later rounds touch few lanes: leave before staging the tables when none of this CTA's lanes is due
+        const uint32_t jj = cta.seg_first + tid;
+        const bool due = jj + 1u < n_sub && stamps[im.sub_first + jj] == round - 1u;
+        if (!__syncthreads_or(due)) return;
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (uint32_t k = tid; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    uint32_t sm_lut;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
+    const uint32_t j = cta.seg_first + tid;
+    SubRec *rec = recs + im.sub_first;
+    uint32_t *stamp = stamps + im.sub_first;
+    const uint8_t *base = clean + im.raw_off;
+    if (round == 0u)
+    {
+        if (j >= n_sub) return;
+        const WalkState s = {j * (uint32_t)(kSubBytes * 8), 0u, 0u};
+        const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((j + 1u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
+        store_rec(rec + j, r);
+        stamp[j] = 0u;
+        return;
+    }
+    if (j + 1u >= n_sub) return;
+    if (round > 1u && stamp[j] != round - 1u) return;
+    const uint2 in = *reinterpret_cast<const uint2 *>(rec + j);
+    const uint2 old = *reinterpret_cast<const uint2 *>(rec + j + 1);
+    const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
+    const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((j + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
+    store_rec(rec + j + 1, r);
+    if (r.p != old.x || r.cz != old.y)
+    {
+        stamp[j + 1] = round;
+        atomicAdd(&stats[round], 1u);   // how many exit states this round still changed (convergence evidence)
+    }
+}
+
+// One warp per image: in-order repair of whatever the last parallel round still changed.
+__global__ void __launch_bounds__(32)
+k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
+             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
+             uint32_t *__restrict__ stamps, uint32_t last_round, uint32_t *__restrict__ stats)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
+    const uint32_t lane = threadIdx.x;
+    const uint32_t img = sync_imgs[blockIdx.x];
+    const ImgDev &im = imgs[img];
+    const uint32_t bits = clean_len[img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    SubRec *rec = recs + im.sub_first;
+    uint32_t *stamp = stamps + im.sub_first;
+    const uint8_t *base = clean + im.raw_off;
+    bool lut_ready = false;
+    uint32_t sm_lut = 0;
+    for (uint32_t b0 = 0; b0 + 1u < n_sub; b0 += 32u)
+    {
+        const uint32_t j = b0 + lane;
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, j + 1u < n_sub && stamp[j] == last_round);
+        while (mask)
+        {
+            if (!lut_ready)
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
+                uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+                for (uint32_t k = lane; k < im.lut_len / 8; k += 32u) dst[k] = __ldg(src + k);
+                __syncwarp();
+                asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
+                lut_ready = true;
+            }
+            uint32_t k = b0 + (uint32_t)__ffs(mask) - 1u;
+            mask &= mask - 1u;
+            if (lane == 0)
+            {
+                // chase the change downstream until the stored state is reproduced
+                while (k + 1u < n_sub)
+                {
+                    const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
+                    const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
+                    const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
+                    const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
+                    store_rec(rec + k + 1, r);
+                    stamp[k] = 0u;
+                    atomicAdd(&stats[7], 1u);   // sub-sequences re-walked by the sequential sweep
+                    if (r.p == old.x && r.cz == old.y) break;
+                    k++;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// One CTA per image: exclusive prefix of (blocks started, DC sums) over its sub-sequence records.
+__global__ void __launch_bounds__(256)
+k_sync_scan(const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs, const uint32_t *__restrict__ clean_len,
+            const SubRec *__restrict__ recs, SubPre *__restrict__ pres)
+{
+    __shared__ uint32_t s_blk[256];
+    __shared__ int32_t s_dc[3][256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t img = sync_imgs[blockIdx.x];
+    const ImgDev &im = imgs[img];
+    const uint32_t bits = clean_len[img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    const SubRec *rec = recs + im.sub_first;
+    SubPre *pre = pres + im.sub_first;
+    const uint32_t per = (n_sub + 255u) / 256u;
+    const uint32_t j0 = min(tid * per, n_sub), j1 = min(j0 + per, n_sub);
+    uint32_t blk = 0;
+    int32_t d0 = 0, d1 = 0, d2 = 0;
+    for (uint32_t j = j0; j < j1; j++)
+    {
+        const uint4 a = reinterpret_cast<const uint4 *>(rec + j)[0];
+        const uint2 b = reinterpret_cast<const uint2 *>(rec + j)[2];
+        blk += a.z; d0 += (int32_t)a.w; d1 += (int32_t)b.x; d2 += (int32_t)b.y;
+    }
+    s_blk[tid] = blk; s_dc[0][tid] = d0; s_dc[1][tid] = d1; s_dc[2][tid] = d2;
+    __syncthreads();
+    if (tid == 0)   // 256 partial sums: a serial exclusive scan is cheap enough
+    {
+        uint32_t rb = 0; int32_t r0 = 0, r1 = 0, r2 = 0;
+        for (int k = 0; k < 256; k++)
+        {
+            const uint32_t tb = s_blk[k]; const int32_t t0 = s_dc[0][k], t1 = s_dc[1][k], t2 = s_dc[2][k];
+            s_blk[k] = rb; s_dc[0][k] = r0; s_dc[1][k] = r1; s_dc[2][k] = r2;
+            rb += tb; r0 += t0; r1 += t1; r2 += t2;
+        }
+    }
+    __syncthreads();
+    blk = s_blk[tid]; d0 = s_dc[0][tid]; d1 = s_dc[1][tid]; d2 = s_dc[2][tid];
+    for (uint32_t j = j0; j < j1; j++)
+    {
+        const uint4 a = reinterpret_cast<const uint4 *>(rec + j)[0];
+        const uint2 b = reinterpret_cast<const uint2 *>(rec + j)[2];
+        uint4 o; o.x = blk; o.y = (uint32_t)d0; o.z = (uint32_t)d1; o.w = (uint32_t)d2;
+        *reinterpret_cast<uint4 *>(pre + j) = o;
+        blk += a.z; d0 += (int32_t)a.w; d1 += (int32_t)b.x; d2 += (int32_t)b.y;
+    }
 }
 
 // =====================================================================================
@@ -1051,13 +1340,16 @@ size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    const int hb = (int)huff_smem_bytes(max_lut_len);
+    cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    e = cudaFuncSetAttribute(k_huff_decode<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    e = cudaFuncSetAttribute(k_huff_decode<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huff_smem_bytes(max_lut_len));
+    e = cudaFuncSetAttribute(k_sync_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_idct_csc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
     if (e != cudaSuccess) return e;
@@ -1080,15 +1372,26 @@ void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
     const uint32_t n = r.cta1 - r.cta0;
     if (n == 0) return;
     const size_t sm = huff_smem_bytes(a.max_lut_len);
-#define B2J_HUFF_LAUNCH(W, D) k_huff_decode<W, D><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts, a.coef, a.status)
-    switch (a.huff_variant & 3u)
-    {
-    case 0: B2J_HUFF_LAUNCH(false, false); break;
-    case 1: B2J_HUFF_LAUNCH(true, false); break;
-    case 2: B2J_HUFF_LAUNCH(false, true); break;
-    default: B2J_HUFF_LAUNCH(true, true); break;
-    }
-#undef B2J_HUFF_LAUNCH
+    if (a.huff_variant & 2u)
+        k_huff_decode<false, true, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
+                                                                    a.coef, a.status, nullptr, nullptr);
+    else
+        k_huff_decode<false, false, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
+                                                                     a.coef, a.status, nullptr, nullptr);
+}
+
+// Streams without restart markers: kSyncRounds + 1 walk passes, the sweep, the scan, then the decode.
+void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
+{
+    const uint32_t n = r.scta1 - r.scta0, ni = r.simg1 - r.simg0;
+    if (n == 0 || ni == 0) return;
+    const size_t lut_bytes = (size_t)a.max_lut_len * 2;
+    for (uint32_t round = 0; round <= (uint32_t)kSyncRounds; round++)
+        k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_stats);
+    k_sync_sweep<<<ni, 32, lut_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.stamps, (uint32_t)kSyncRounds, a.sync_stats);
+    k_sync_scan<<<ni, 256, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.recs, a.pres);
+    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
+                                                                                           a.clean_len, a.luts, a.coef, a.status, a.recs, a.pres);
 }
 
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)

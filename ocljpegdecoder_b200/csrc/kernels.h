@@ -16,7 +16,9 @@ struct DecodeArgs
     const uint8_t *raw;
     const ImgDev *imgs;
     const uint32_t *chunk_img;
-    const HuffCtaDev *huff_ctas;
+    const HuffCtaDev *huff_ctas;   // restart-interval path: CTA -> (image, first segment)
+    const HuffCtaDev *sync_ctas;   // self-synchronising path: CTA -> (image, first sub-sequence)
+    const uint32_t *sync_imgs;     // images on the self-synchronising path
     const TileDev *tiles;
     const uint16_t *luts;
     const uint16_t *qtabs;
@@ -25,6 +27,10 @@ struct DecodeArgs
     uint8_t *clean;
     uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;
     uint32_t *clean_len, *seg_start;
+    SubRec *recs;       // self-synchronising path: one record per sub-sequence
+    SubPre *pres;
+    uint32_t *stamps;
+    uint32_t *sync_stats;   // [r] = exit states changed in round r, [7] = sub-sequences re-walked by the sweep
     // outputs
     int16_t *coef;
     uint8_t *pixels;
@@ -36,13 +42,15 @@ struct DecodeArgs
 };
 
 // A contiguous group of images of a batch: the unit the two-stream pipeline works on.
-struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1; };
+struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1, scta0, scta1, simg0, simg1; };
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
 size_t huff_smem_bytes(uint32_t max_lut_len);
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
+void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // kSyncRounds + 4 kernels
+constexpr int kSyncLaunches = kSyncRounds + 4;
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s);      // 1 kernel
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s);
 

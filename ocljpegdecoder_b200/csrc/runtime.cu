@@ -107,11 +107,11 @@ struct b2j_batch
     uint8_t *h_blob; size_t h_blob_cap;
     uint8_t *d_blob; size_t d_blob_cap;
     size_t blob_bytes;
-    size_t off_imgs, off_chunk_img, off_ctas, off_tiles, off_luts, off_qtabs, off_raw;
+    size_t off_imgs, off_chunk_img, off_ctas, off_sctas, off_simgs, off_tiles, off_luts, off_qtabs, off_raw;
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -284,7 +284,11 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
 
     std::vector<uint32_t> chunk_img;
     std::vector<uint32_t> img_cta0((size_t)n + 1), img_tile0((size_t)n + 1), img_chunk0((size_t)n + 1);
-    std::vector<HuffCtaDev> ctas;
+    std::vector<HuffCtaDev> ctas;    // restart-interval path
+    std::vector<HuffCtaDev> sctas;   // self-synchronising path (no DRI)
+    std::vector<uint32_t> simgs;
+    std::vector<uint32_t> img_scta0((size_t)n + 1), img_simg0((size_t)n + 1);
+    uint32_t sub_total = 0;
     std::vector<TileDev> tiles;
     std::vector<uint16_t> luts;
     std::vector<uint16_t> qtabs((size_t)n * 192);
@@ -304,6 +308,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             d.scan_size >= 0xFFFF0000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
         { rc = B2J_E_ARG; break; }
         img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
+        img_scta0[(size_t)i] = (uint32_t)sctas.size(); img_simg0[(size_t)i] = (uint32_t)simgs.size();
         im.raw_off = raw_total;
         im.raw_len = (uint32_t)d.scan_size;
         raw_total += align_up((size_t)im.raw_len + 32, 16);
@@ -319,7 +324,18 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         im.seg_first = seg_total;
         im.n_segs = (im.mcu_count + im.restart_interval - 1) / im.restart_interval;
         seg_total += im.n_segs;
-        for (uint32_t s = 0; s < im.n_segs; s += kHuffThreads) ctas.push_back({(uint32_t)i, s});
+        if (im.has_dri)
+            for (uint32_t s = 0; s < im.n_segs; s += kHuffThreads) ctas.push_back({(uint32_t)i, s});
+        else
+        {
+            // no restart markers: self-synchronising sub-sequence decode, one lane per kSubBytes of stream
+            im.sub_first = sub_total;
+            im.n_sub_max = (im.raw_len + kSubBytes - 1) / kSubBytes;
+            if (im.n_sub_max == 0) im.n_sub_max = 1;
+            sub_total += im.n_sub_max;
+            for (uint32_t s = 0; s < im.n_sub_max; s += kHuffThreads) sctas.push_back({(uint32_t)i, s});
+            simgs.push_back((uint32_t)i);
+        }
         im.blk_first = (uint32_t)blk_total;
         im.blk_count = (uint32_t)d.blk_count;
         blk_total += (size_t)d.blk_count;
@@ -377,6 +393,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     if (rc != B2J_OK) { delete b; return rc; }
     if (blk_total + kTileBlocks >= 0xFFFFFFF0ull) { delete b; return B2J_E_ARG; }
     img_cta0[(size_t)n] = (uint32_t)ctas.size(); img_tile0[(size_t)n] = (uint32_t)tiles.size(); img_chunk0[(size_t)n] = (uint32_t)chunk_img.size();
+    img_scta0[(size_t)n] = (uint32_t)sctas.size(); img_simg0[(size_t)n] = (uint32_t)simgs.size();
     {
         // contiguous groups of images with similar block counts: the units of the two-stream pipeline
         const int np = ctx->n_parts < n ? ctx->n_parts : n;
@@ -388,7 +405,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             while (i1 < n && (i1 == i0 || (size_t)b->imgs[(size_t)i1].blk_first + b->imgs[(size_t)i1].blk_count <= target) && n - i1 > np - p - 1) i1++;
             if (p == np - 1) i1 = n;
             b->parts.push_back({(uint32_t)i0, (uint32_t)i1, img_chunk0[(size_t)i0], img_chunk0[(size_t)i1], img_cta0[(size_t)i0], img_cta0[(size_t)i1],
-                                img_tile0[(size_t)i0], img_tile0[(size_t)i1]});
+                                img_tile0[(size_t)i0], img_tile0[(size_t)i1], img_scta0[(size_t)i0], img_scta0[(size_t)i1],
+                                img_simg0[(size_t)i0], img_simg0[(size_t)i1]});
             i0 = i1;
         }
         b->ev_huff.resize(b->parts.size());
@@ -406,6 +424,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_imgs = place(sizeof(ImgDev) * (size_t)n);
     b->off_chunk_img = place(sizeof(uint32_t) * chunk_img.size());
     b->off_ctas = place(sizeof(HuffCtaDev) * ctas.size());
+    b->off_sctas = place(sizeof(HuffCtaDev) * sctas.size());
+    b->off_simgs = place(sizeof(uint32_t) * simgs.size());
     b->off_tiles = place(sizeof(TileDev) * tiles.size());
     b->off_luts = place(sizeof(uint16_t) * luts.size());
     b->off_qtabs = place(sizeof(uint16_t) * qtabs.size());
@@ -422,6 +442,10 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_clean_len = place(4 * (size_t)n);
     b->off_seg_start = place(4 * (size_t)seg_total);
     b->off_status = place(4 * (size_t)n);
+    b->off_recs = place(sizeof(SubRec) * (size_t)sub_total);
+    b->off_pres = place(sizeof(SubPre) * (size_t)sub_total);
+    b->off_stamps = place(4 * (size_t)sub_total);
+    b->off_sync_stats = place(4 * 8);
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
     b->coef_rows = blk_total + kTileBlocks;   // one tile of padding: the last tile may read past the last block
@@ -446,6 +470,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     memcpy(b->h_blob + b->off_imgs, b->imgs.data(), sizeof(ImgDev) * (size_t)n);
     memcpy(b->h_blob + b->off_chunk_img, chunk_img.data(), sizeof(uint32_t) * chunk_img.size());
     memcpy(b->h_blob + b->off_ctas, ctas.data(), sizeof(HuffCtaDev) * ctas.size());
+    memcpy(b->h_blob + b->off_sctas, sctas.data(), sizeof(HuffCtaDev) * sctas.size());
+    memcpy(b->h_blob + b->off_simgs, simgs.data(), sizeof(uint32_t) * simgs.size());
     memcpy(b->h_blob + b->off_tiles, tiles.data(), sizeof(TileDev) * tiles.size());
     memcpy(b->h_blob + b->off_luts, luts.data(), sizeof(uint16_t) * luts.size());
     memcpy(b->h_blob + b->off_qtabs, qtabs.data(), sizeof(uint16_t) * qtabs.size());
@@ -467,6 +493,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.imgs = reinterpret_cast<const ImgDev *>(b->d_blob + b->off_imgs);
     a.chunk_img = reinterpret_cast<const uint32_t *>(b->d_blob + b->off_chunk_img);
     a.huff_ctas = reinterpret_cast<const HuffCtaDev *>(b->d_blob + b->off_ctas);
+    a.sync_ctas = reinterpret_cast<const HuffCtaDev *>(b->d_blob + b->off_sctas);
+    a.sync_imgs = reinterpret_cast<const uint32_t *>(b->d_blob + b->off_simgs);
+    a.recs = reinterpret_cast<SubRec *>(b->d_scratch + b->off_recs);
+    a.pres = reinterpret_cast<SubPre *>(b->d_scratch + b->off_pres);
+    a.stamps = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_stamps);
+    a.sync_stats = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_stats);
     a.tiles = reinterpret_cast<const TileDev *>(b->d_blob + b->off_tiles);
     a.luts = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_luts);
     a.qtabs = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_qtabs);
@@ -495,7 +527,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b2j_batch_info &inf = b->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_images = n;
-    inf.kernel_launches = 5 * (int32_t)b->parts.size();
+    inf.kernel_launches = (int32_t)b->parts.size() * (4 + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
     inf.scan_bytes = scan_bytes;
@@ -559,6 +591,7 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
     if (ev) CU_TRY(cudaEventRecord(ev[0], s));
     CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
     CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
+    CU_TRY(cudaMemsetAsync(a.sync_stats, 0, 4 * 8, s));
     const size_t np = b->parts.size();
     for (size_t p = 0; p < np; p++)
     {
@@ -568,6 +601,7 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
         launch_prepass(a, r, s);
         if (pe) CU_TRY(cudaEventRecord(pe[1], s));
         launch_huffman(a, r, s);
+        launch_huffman_sync(a, r, s);
         if (pe) CU_TRY(cudaEventRecord(pe[2], s));
         if (np == 1)
         {
@@ -655,6 +689,16 @@ extern "C" int b2j_batch_status(b2j_batch *b, void *stream, int32_t *status)
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t s = pick_stream(b, stream);
     CU_TRY(cudaMemcpyAsync(status, b->args.status, 4 * (size_t)b->n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_sync_stats(b2j_batch *b, void *stream, uint32_t *out8)
+{
+    if (!b || !out8) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    CU_TRY(cudaMemcpyAsync(out8, b->args.sync_stats, 4 * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     return B2J_OK;
 }

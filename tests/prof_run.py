@@ -19,5 +19,6 @@ batch.upload()
 per, total = batch.decode_steps(steps)
 st = batch.status()
 assert not st.any(), st
+print("sync stats", batch.sync_stats().tolist(), "blocks", batch.info().total_blocks)
 print("steps %d total %.3f ms; last step: prepass %.3f huffman %.3f idct %.3f" % (
     steps, total, per[steps - 1].prepass_ms, per[steps - 1].huffman_ms, per[steps - 1].idct_ms))
