@@ -263,3 +263,51 @@ def test_other_baseline_configs(decoder, oracle, cfg, count):
             _check_pixels(pix[i], bgra)
     finally:
         oracle.set_strict(True)
+
+
+def test_selfsync_streams_without_restart_markers(decoder, oracle):
+    """Streams without DRI take the self-synchronising sub-sequence decoder: quality 100 makes blocks that
+    are longer than a whole 1024-bit sub-sequence, quality 5 makes sub-sequences with dozens of blocks."""
+    specs = [(257, 129, "420", 100), (257, 129, "444", 100), (640, 360, "422", 5), (640, 360, "420", 5),
+             (1024, 768, "444", 92), (333, 777, "420", 60)]
+    files = [synth.synth_jpeg(w, h, 900 + i, q, ss, 0, optimize=(i % 2 == 0)) for i, (w, h, ss, q) in enumerate(specs)]
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    stats = batch.sync_stats()
+    n_sub = sum((len(f) + 127) // 128 for f in files)
+    print("sync stats", stats.tolist(), "sub-sequences", n_sub)
+    # round 1 corrects guessed states; with blocks longer than a sub-sequence (quality 100) the guesses
+    # converge slowly and the in-order sweep -- the correctness safety net -- finishes the job
+    assert stats[1] > 0 and stats[7] < n_sub
+    oracle.set_strict(False)
+    try:
+        for i, f in enumerate(files):
+            rc, _, coef, bgra = oracle.decode(f)
+            assert rc == 0
+            assert np.array_equal(batch.coefs(i), coef)
+            _check_pixels(batch.pixels(i), bgra)
+    finally:
+        oracle.set_strict(True)
+    batch.close()
+
+
+def test_selfsync_corrupt_streams_are_flagged(decoder, oracle):
+    good = synth.synth_jpeg(320, 240, 6, 90, "420", 0)
+    rc, d = oracle.parse(good)
+    off = d.scan_offset
+    cases = {"truncated": good[:off + (len(good) - off) // 2]}
+    b = bytearray(good)
+    mid = off + (len(good) - off) // 3
+    for j in range(24):
+        if b[mid + j] != 0xFF and b[mid + j - 1] != 0xFF:
+            b[mid + j] ^= 0x5A
+    cases["bitflips"] = bytes(b)
+    names = sorted(cases)
+    st, _, _ = _decode(decoder, [cases[n] for n in names] + [good])
+    assert st[-1] == 0
+    for n, s in zip(names, st[:-1]):
+        rc, *_ = oracle.decode(cases[n], want_pixels=False)
+        if rc != 0:
+            assert s != 0, "%s: the reference path fails but the GPU status is clean" % n
