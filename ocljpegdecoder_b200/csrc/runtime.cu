@@ -772,30 +772,72 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
                                uint8_t *const *out_bgra, int32_t *status)
 {
     if (!ctx || n <= 0 || !files || !lens || !out_bgra || !status) return B2J_E_ARG;
-    std::vector<b2j_image_desc> descs;
-    std::vector<const uint8_t *> f;
-    std::vector<size_t> l;
-    std::vector<uint8_t *> o;
-    std::vector<int> idx;
-    descs.reserve((size_t)n);
+    CU_TRY(cudaSetDevice(ctx->device));
+    // Pipelined over groups of images: while group g's pixels travel device->host on the second stream,
+    // group g+1 is parsed and staged on the host, uploaded and decoded on the first stream. The D2H copy
+    // of the BGRA pixels is what bounds this call (PCIe), everything else hides behind it.
+    std::vector<b2j_image_desc> descs((size_t)n);
+    std::vector<int> ok_idx;
+    ok_idx.reserve((size_t)n);
     for (int i = 0; i < n; i++)
     {
-        b2j_image_desc d;
-        const int rc = b2j_parse_header(files[i], lens[i], gate, &d);
+        const int rc = b2j_parse_header(files[i], lens[i], gate, &descs[(size_t)i]);
         status[i] = rc;
-        if (rc != B2J_OK) continue;
-        descs.push_back(d); f.push_back(files[i]); l.push_back(lens[i]); o.push_back(out_bgra[i]); idx.push_back(i);
+        if (rc == B2J_OK) ok_idx.push_back(i);
     }
-    if (descs.empty()) return B2J_OK;
-    b2j_batch *b = nullptr;
-    int rc = b2j_batch_create(ctx, (int)descs.size(), descs.data(), f.data(), l.data(), &b);
-    if (rc != B2J_OK) return rc;
-    std::vector<int32_t> st(descs.size());
-    if ((rc = b2j_batch_upload(b, nullptr)) == B2J_OK && (rc = b2j_batch_decode(b, nullptr)) == B2J_OK &&
-        (rc = b2j_batch_read_all_pixels(b, nullptr, o.data())) == B2J_OK && (rc = b2j_batch_status(b, nullptr, st.data())) == B2J_OK)
+    if (ok_idx.empty()) return B2J_OK;
+    const char *ge = getenv("B2J_HOST_GROUP");
+    size_t group = ge ? (size_t)atoi(ge) : 16;   // measured on B200: 16 images per group reaches the PCIe D2H floor
+    if (group < 1) group = 1;
+    struct Group { b2j_batch *b; size_t first, count; cudaEvent_t decoded; };
+    std::vector<Group> groups;
+    int rc = B2J_OK;
+    for (size_t g0 = 0; g0 < ok_idx.size() && rc == B2J_OK; g0 += group)
     {
-        for (size_t k = 0; k < idx.size(); k++) status[idx[k]] = st[k];
+        const size_t cnt = ok_idx.size() - g0 < group ? ok_idx.size() - g0 : group;
+        std::vector<b2j_image_desc> d(cnt);
+        std::vector<const uint8_t *> f(cnt);
+        std::vector<size_t> l(cnt);
+        for (size_t k = 0; k < cnt; k++)
+        {
+            const int i = ok_idx[g0 + k];
+            d[k] = descs[(size_t)i]; f[k] = files[i]; l[k] = lens[i];
+        }
+        Group gr{nullptr, g0, cnt, nullptr};
+        rc = b2j_batch_create(ctx, (int)cnt, d.data(), f.data(), l.data(), &gr.b);
+        if (rc != B2J_OK) break;
+        groups.push_back(gr);
+        Group &G = groups.back();
+        if ((rc = b2j_batch_upload(G.b, ctx->stream)) != B2J_OK) break;
+        if ((rc = b2j_batch_decode(G.b, ctx->stream)) != B2J_OK) break;
+        cudaError_t e = cudaEventCreateWithFlags(&G.decoded, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(G.decoded, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, G.decoded, 0);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "event"); break; }
+        for (size_t k = 0; k < cnt && rc == B2J_OK; k++)
+        {
+            const ImgDev &im = G.b->imgs[k];
+            uint8_t *dst = out_bgra[ok_idx[g0 + k]];
+            if (!dst) continue;
+            e = cudaMemcpyAsync(dst, G.b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, ctx->stream2);
+            if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyAsync D2H");
+        }
     }
-    b2j_batch_destroy(b);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream2);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+    if (rc == B2J_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail_cuda(e1 != cudaSuccess ? e1 : e2, "cudaStreamSynchronize");
+    for (Group &G : groups)
+    {
+        if (rc == B2J_OK)
+        {
+            std::vector<int32_t> st(G.count);
+            const int r2 = b2j_batch_status(G.b, ctx->stream, st.data());
+            if (r2 != B2J_OK) rc = r2;
+            else
+                for (size_t k = 0; k < G.count; k++) status[ok_idx[G.first + k]] = st[k];
+        }
+        if (G.decoded) cudaEventDestroy(G.decoded);
+        b2j_batch_destroy(G.b);
+    }
     return rc;
 }
