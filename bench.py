@@ -189,6 +189,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)[kernel])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -322,7 +331,7 @@ def main():
                        "l2": "no explicit flush: every step streams %.2f GB per GPU (>> 126 MB L2)" % (info.algorithmic_bytes / 1e9),
                        "parallelism": "images sharded by rank, no collective"},
             "roofline": {"bound": "hbm", "kernel": kb[dom][0], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(kb[dom][0]), "peak_source": peak_src,
                          "bytes_per_launch": kb[dom][1], "launch_ms": round(stage[dom], 4),
                          "pipeline": {"achieved": round(pipe, 1), "frac": round(pipe / peak, 4),
                                       "note": "all 5 kernels: (C + 2*128*B + 4*W*H) / step time, SURVEY.md 8(d)"},
