@@ -168,6 +168,19 @@ B2J_HD int32_t csc_g_off(int32_t U, int32_t V)
 }
 B2J_HD int32_t csc_g_fix(int32_t Y, int32_t U, int32_t V) { return (U == -200 && V == 200 && Y >= 188) ? 1 : 0; }
 
+// The kernel keeps the IDCT samples biased by +256 (0..511, unsigned 16 bit: the bias rides on the DC
+// term of the column pass for free and makes the clip a single packed min). The same offsets for
+// biased inputs Yb = Y+256, Ub = U+256, Vb = V+256, such that Yb + off_b == Y + off:
+//     r: 128 + floor(91881*(Vb-256) / 65536) - 256, and likewise b and g, constants folded.
+B2J_HD int32_t csc_r_off_b(int32_t Vb) { return (91881 * Vb - 91881 * 256 - 128 * 65536) >> 16; }
+B2J_HD int32_t csc_b_off_b(int32_t Ub) { return (116130 * Ub + 64 - 116130 * 256 - 128 * 65536) >> 16; }
+B2J_HD int32_t csc_g_off_b(int32_t Ub, int32_t Vb)
+{
+    const uint32_t x = (uint32_t)(27100000 + 256 * (34414 + 71414) - (34414 * Ub + 71414 * Vb));
+    return (int32_t)(x / 100000u) - 271 + 128 - 256;
+}
+B2J_HD int32_t csc_g_fix_b(int32_t Yb, int32_t Ub, int32_t Vb) { return (Ub == 56 && Vb == 456 && Yb >= 444) ? 1 : 0; }
+
 B2J_HD uint32_t clamp255(int32_t n) { return n < 0 ? 0u : (n > 255 ? 255u : (uint32_t)n); }
 
 // One pixel, the scalar form (edges, odd widths, and the host-side exhaustive check).
@@ -177,6 +190,15 @@ B2J_HD uint32_t csc_pixel(int32_t Y, int32_t U, int32_t V)
     const uint32_t r = clamp255(Y + csc_r_off(V));
     const uint32_t g = clamp255(Y + csc_g_off(U, V) - csc_g_fix(Y, U, V));
     const uint32_t b = clamp255(Y + csc_b_off(U));
+    return (r << 16) | (g << 8) | b;
+}
+
+// One pixel from biased samples (what the colour phase of the kernel computes).
+B2J_HD uint32_t csc_pixel_biased(int32_t Yb, int32_t Ub, int32_t Vb)
+{
+    const uint32_t r = clamp255(Yb + csc_r_off_b(Vb));
+    const uint32_t g = clamp255(Yb + csc_g_off_b(Ub, Vb) - csc_g_fix_b(Yb, Ub, Vb));
+    const uint32_t b = clamp255(Yb + csc_b_off_b(Ub));
     return (r << 16) | (g << 8) | b;
 }
 

@@ -976,13 +976,14 @@ __device__ __forceinline__ uint32_t addclamp2(uint32_t a, uint32_t b)
     return __viaddmin_s16x2_relu(a, b, 0x00FF00FFu);
 }
 
-// int32 pair -> int16 pair with saturation, then the reference's clip to [-256,255] on both halves
-// (cpuIDCT8x8.cpp:13-23). Saturating to int16 first cannot change a value that is clipped to 9 bits.
+// Two column-pass outputs that already carry the +256 bias -> one word of two unsigned 16-bit samples
+// clipped to [0, 511], i.e. the reference's clip to [-256, 255] (cpuIDCT8x8.cpp:13-23): the pack
+// saturates below 0 (and above 65535), the packed min cuts at 511.
 __device__ __forceinline__ uint32_t pack_clip2(int32_t lo, int32_t hi)
 {
     uint32_t d;
-    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
-    return __vmins2(__vmaxs2(d, 0xFF00FF00u), 0x00FF00FFu);
+    asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return __vminu2(d, 0x01FF01FFu);
 }
 
 // Layout constants of a tile for luma sampling RH x RV (chroma 1x1):
@@ -1022,35 +1023,36 @@ struct TileSmem
 };
 
 // Chroma offsets of one pixel pair, packed as two int16: the pair shares one sample when RH == 2.
+// Samples in the tile are biased by +256 (0..511), see csc_*_off_b in b2j_math.h.
 template <int RH>
 __device__ __forceinline__ void chroma_offsets(uint32_t cb, uint32_t cr, uint32_t &ro, uint32_t &go, uint32_t &bo, bool &special)
 {
-    const int32_t u0 = (int16_t)(cb & 0xFFFFu), v0 = (int16_t)(cr & 0xFFFFu);
+    const int32_t u0 = (int32_t)(cb & 0xFFFFu), v0 = (int32_t)(cr & 0xFFFFu);
     if (RH == 2)
     {
-        ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) * 0x10001u;
-        go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) * 0x10001u;
-        bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) * 0x10001u;
-        special = ((cb & 0xFFFFu) == 0xFF38u) & ((cr & 0xFFFFu) == 0x00C8u);   // U = -200, V = 200
+        ro = __byte_perm((uint32_t)csc_r_off_b(v0), 0, 0x1010);
+        go = __byte_perm((uint32_t)csc_g_off_b(u0, v0), 0, 0x1010);
+        bo = __byte_perm((uint32_t)csc_b_off_b(u0), 0, 0x1010);
+        special = ((cb & 0xFFFFu) == 56u) & ((cr & 0xFFFFu) == 456u);   // U = -200, V = 200
     }
     else
     {
-        const int32_t u1 = (int32_t)cb >> 16, v1 = (int32_t)cr >> 16;
-        ro = (uint32_t)(csc_r_off(v0) & 0xFFFF) | ((uint32_t)csc_r_off(v1) << 16);
-        go = (uint32_t)(csc_g_off(u0, v0) & 0xFFFF) | ((uint32_t)csc_g_off(u1, v1) << 16);
-        bo = (uint32_t)(csc_b_off(u0) & 0xFFFF) | ((uint32_t)csc_b_off(u1) << 16);
-        special = (((cb & 0xFFFFu) == 0xFF38u) & ((cr & 0xFFFFu) == 0x00C8u)) | (((cb >> 16) == 0xFF38u) & ((cr >> 16) == 0x00C8u));
+        const int32_t u1 = (int32_t)(cb >> 16), v1 = (int32_t)(cr >> 16);
+        ro = __byte_perm((uint32_t)csc_r_off_b(v0), (uint32_t)csc_r_off_b(v1), 0x5410);
+        go = __byte_perm((uint32_t)csc_g_off_b(u0, v0), (uint32_t)csc_g_off_b(u1, v1), 0x5410);
+        bo = __byte_perm((uint32_t)csc_b_off_b(u0), (uint32_t)csc_b_off_b(u1), 0x5410);
+        special = (((cb & 0xFFFFu) == 56u) & ((cr & 0xFFFFu) == 456u)) | (((cb >> 16) == 56u) & ((cr >> 16) == 456u));
     }
 }
 
 // The one double-rounding case of the reference (b2j_math.h): recompute G of a pixel pair the slow way.
 __device__ __noinline__ uint32_t green_special(uint32_t yy, uint32_t cb, uint32_t cr)
 {
-    const int32_t ya = (int16_t)(yy & 0xFFFFu), yb = (int32_t)yy >> 16;
-    const int32_t u0 = (int16_t)(cb & 0xFFFFu), u1 = (int32_t)cb >> 16;
-    const int32_t v0 = (int16_t)(cr & 0xFFFFu), v1 = (int32_t)cr >> 16;
-    const uint32_t ga = clamp255(ya + csc_g_off(u0, v0) - csc_g_fix(ya, u0, v0));
-    const uint32_t gb = clamp255(yb + csc_g_off(u1, v1) - csc_g_fix(yb, u1, v1));
+    const int32_t ya = (int32_t)(yy & 0xFFFFu), yb = (int32_t)(yy >> 16);
+    const int32_t u0 = (int32_t)(cb & 0xFFFFu), u1 = (int32_t)(cb >> 16);
+    const int32_t v0 = (int32_t)(cr & 0xFFFFu), v1 = (int32_t)(cr >> 16);
+    const uint32_t ga = clamp255(ya + csc_g_off_b(u0, v0) - csc_g_fix_b(ya, u0, v0));
+    const uint32_t gb = clamp255(yb + csc_g_off_b(u1, v1) - csc_g_fix_b(yb, u1, v1));
     return ga | (gb << 16);
 }
 
@@ -1188,9 +1190,14 @@ __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const Ti
         v[8 * r + 7] = ((int32_t)cw.w >> 16) * (int32_t)qb.w;
         idct_row(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
     }
+    // the +256 sample bias enters through the DC row: the column pass computes (b0*256 + 8192 + ...) >> 14, and
+    // 256 << 14 == 16384 * 256, so adding 16384 to b0 adds exactly 256 to all eight outputs of the column
 #pragma unroll
     for (int c = 0; c < 8; c++)
+    {
+        v[c] += 16384;
         idct_col_noclip(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c], v[56 + c]);
+    }
 #pragma unroll
     for (int r = 0; r < 8; r++)
     {

@@ -31,7 +31,7 @@ long chk_csc_exhaustive(int32_t first_bad[3])
     for (int y = -256; y < 256; y++)
         for (int u = -256; u < 256; u++)
             for (int v = -256; v < 256; v++)
-                if (b2j::csc_pixel(y, u, v) != ref_pixel(y, u, v))
+                if (b2j::csc_pixel(y, u, v) != ref_pixel(y, u, v) || b2j::csc_pixel_biased(y + 256, u + 256, v + 256) != ref_pixel(y, u, v))
                 {
                     if (!bad) { first_bad[0] = y; first_bad[1] = u; first_bad[2] = v; }
                     bad++;
