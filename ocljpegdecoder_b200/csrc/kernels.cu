@@ -1162,7 +1162,25 @@ __device__ __forceinline__ TileSmem *tile_smem()
 
 // Dequantise + IDCT of one block per thread, in place in the swizzled tile (decoder.cpp:340,
 // cpuIDCT8x8.cpp:25-127).
-template <int RH, int RV>
+// signed 16-bit x unsigned 8-bit dot product of two lanes: a.lo*b.b0 + a.hi*b.b1 (+0) and a.lo*b.b2 + a.hi*b.b3
+__device__ __forceinline__ int32_t dp2a_lo(uint32_t a, uint32_t b)
+{
+    int32_t d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+__device__ __forceinline__ int32_t dp2a_hi(uint32_t a, uint32_t b)
+{
+    int32_t d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+
+// NARROWQ (every quantiser of the batch < 256, i.e. all 8-bit DQTs): the table holds one word per
+// coefficient pair, q_even | q_odd << 24, and one dp2a per coefficient unpacks the int16 AND multiplies:
+// dp2a.lo = c_even*q_even + c_odd*0, dp2a.hi = c_even*0 + c_odd*q_odd. Otherwise 32-bit quantisers and a
+// separate unpack + multiply.
+template <int RH, int RV, bool NARROWQ>
 __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const TileSide &sd)
 {
     using G = TileGeom<RH, RV>;
@@ -1177,17 +1195,28 @@ __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const Ti
     for (int r = 0; r < 8; r++)
     {
         const uint4 cw = *reinterpret_cast<const uint4 *>(rowp + ((r ^ sw) << 4));
-        const uint4 qa = *reinterpret_cast<const uint4 *>(q + 8 * r);
-        const uint4 qb = *reinterpret_cast<const uint4 *>(q + 8 * r + 4);
         // decoder.cpp:340: int32 product of the decoded value and the quantiser
-        v[8 * r + 0] = (int32_t)(int16_t)(cw.x & 0xFFFFu) * (int32_t)qa.x;
-        v[8 * r + 1] = ((int32_t)cw.x >> 16) * (int32_t)qa.y;
-        v[8 * r + 2] = (int32_t)(int16_t)(cw.y & 0xFFFFu) * (int32_t)qa.z;
-        v[8 * r + 3] = ((int32_t)cw.y >> 16) * (int32_t)qa.w;
-        v[8 * r + 4] = (int32_t)(int16_t)(cw.z & 0xFFFFu) * (int32_t)qb.x;
-        v[8 * r + 5] = ((int32_t)cw.z >> 16) * (int32_t)qb.y;
-        v[8 * r + 6] = (int32_t)(int16_t)(cw.w & 0xFFFFu) * (int32_t)qb.z;
-        v[8 * r + 7] = ((int32_t)cw.w >> 16) * (int32_t)qb.w;
+        if (NARROWQ)
+        {
+            const uint4 qp = *reinterpret_cast<const uint4 *>(q + 4 * r);
+            v[8 * r + 0] = dp2a_lo(cw.x, qp.x); v[8 * r + 1] = dp2a_hi(cw.x, qp.x);
+            v[8 * r + 2] = dp2a_lo(cw.y, qp.y); v[8 * r + 3] = dp2a_hi(cw.y, qp.y);
+            v[8 * r + 4] = dp2a_lo(cw.z, qp.z); v[8 * r + 5] = dp2a_hi(cw.z, qp.z);
+            v[8 * r + 6] = dp2a_lo(cw.w, qp.w); v[8 * r + 7] = dp2a_hi(cw.w, qp.w);
+        }
+        else
+        {
+            const uint4 qa = *reinterpret_cast<const uint4 *>(q + 8 * r);
+            const uint4 qb = *reinterpret_cast<const uint4 *>(q + 8 * r + 4);
+            v[8 * r + 0] = (int32_t)(int16_t)(cw.x & 0xFFFFu) * (int32_t)qa.x;
+            v[8 * r + 1] = ((int32_t)cw.x >> 16) * (int32_t)qa.y;
+            v[8 * r + 2] = (int32_t)(int16_t)(cw.y & 0xFFFFu) * (int32_t)qa.z;
+            v[8 * r + 3] = ((int32_t)cw.y >> 16) * (int32_t)qa.w;
+            v[8 * r + 4] = (int32_t)(int16_t)(cw.z & 0xFFFFu) * (int32_t)qb.x;
+            v[8 * r + 5] = ((int32_t)cw.z >> 16) * (int32_t)qb.y;
+            v[8 * r + 6] = (int32_t)(int16_t)(cw.w & 0xFFFFu) * (int32_t)qb.z;
+            v[8 * r + 7] = ((int32_t)cw.w >> 16) * (int32_t)qb.w;
+        }
         idct_row(v[8 * r + 0], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3], v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
     }
     // the +256 sample bias enters through the DC row: the column pass computes (b0*256 + 8192 + ...) >> 14, and
@@ -1210,14 +1239,15 @@ __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const Ti
     }
 }
 
+template <bool NARROWQ>
 __device__ __forceinline__ void idct_dispatch(uint8_t *tilep, const TileSide &sd)
 {
     switch (sd.mode)   // uniform per CTA
     {
-    case kMode444: idct_phase<1, 1>(tilep, sd); break;
-    case kMode420: idct_phase<2, 2>(tilep, sd); break;
-    case kMode422: idct_phase<2, 1>(tilep, sd); break;
-    default:       idct_phase<1, 2>(tilep, sd); break;
+    case kMode444: idct_phase<1, 1, NARROWQ>(tilep, sd); break;
+    case kMode420: idct_phase<2, 2, NARROWQ>(tilep, sd); break;
+    case kMode422: idct_phase<2, 1, NARROWQ>(tilep, sd); break;
+    default:       idct_phase<1, 2, NARROWQ>(tilep, sd); break;
     }
 }
 
@@ -1242,7 +1272,7 @@ __device__ __forceinline__ SideRegs side_load(const ImgDev *__restrict__ imgs, c
 {
     SideRegs r;
     const ImgDev *im = imgs + d.img;
-    r.q = (uint32_t)__ldg(qtabs + (size_t)d.img * 192 + threadIdx.x);
+    r.q = threadIdx.x < 96 ? __ldg(reinterpret_cast<const uint32_t *>(qtabs + (size_t)d.img * 192) + threadIdx.x) : 0u;   // a pair
     r.width = __ldg(&im->width);
     r.height = __ldg(&im->height);
     r.mcu_count_w = __ldg(&im->mcu_count_w);
@@ -1250,11 +1280,17 @@ __device__ __forceinline__ SideRegs side_load(const ImgDev *__restrict__ imgs, c
     return r;
 }
 
+template <bool NARROWQ>
 __device__ __forceinline__ void side_store(TileSide &sd, const TileDev d, const SideRegs &r, uint8_t *__restrict__ pix)
 {
     const uint32_t tid = threadIdx.x;
     const uint32_t n_mcus = d.info >> 8;
-    sd.qt[(tid >> 6) * kQtStride + (tid & 63u)] = r.q;
+    if (tid < 96)
+    {
+        const uint32_t comp = tid >> 5, k = tid & 31u;   // quantiser pair k of component comp
+        if (NARROWQ) sd.qt[comp * kQtStride + k] = (r.q & 0xFFu) | ((r.q >> 16) << 24);
+        else { sd.qt[comp * kQtStride + 2 * k] = r.q & 0xFFFFu; sd.qt[comp * kQtStride + 2 * k + 1] = r.q >> 16; }
+    }
     if (tid < n_mcus)
     {
         const uint32_t gm = d.mcu_first + tid;
@@ -1280,7 +1316,7 @@ __device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMo
 #ifndef B2J_IDCT_MIN_CTAS
 #define B2J_IDCT_MIN_CTAS 5   // measured on B200: 64 registers with ~220 B of spills beats 80 registers at 4 CTAs per SM
 #endif
-template <bool USE_TMA>
+template <bool USE_TMA, bool NARROWQ>
 __global__ void __launch_bounds__(kTileBlocks, B2J_IDCT_MIN_CTAS)
 k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
            const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
@@ -1297,7 +1333,7 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
             mbar_expect_tx(&sm.bar[0], kTileBlocks * 128);
             tma_load_2d(sm.tile[0], &tmap, 0, (int)d.row_first, &sm.bar[0]);
         }
-        side_store(sm.side[0], d, side_load(imgs, qtabs, d), pix);
+        side_store<NARROWQ>(sm.side[0], d, side_load(imgs, qtabs, d), pix);
         __syncthreads();   // barrier initialisation + side data visible
         uint32_t spins = 0;
         while (!mbar_try_wait(&sm.bar[0], 0))
@@ -1319,10 +1355,10 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
             const uint32_t rr = idx >> 3, c = idx & 7u;
             *reinterpret_cast<uint4 *>(sm.tile[0] + rr * 128u + ((c ^ (rr & 7u)) << 4)) = v[k];
         }
-        side_store(sm.side[0], d, r, pix);
+        side_store<NARROWQ>(sm.side[0], d, r, pix);
         __syncthreads();
     }
-    idct_dispatch(sm.tile[0], sm.side[0]);
+    idct_dispatch<NARROWQ>(sm.tile[0], sm.side[0]);
     __syncthreads();
     csc_dispatch(sm.tile[0], sm.side[0]);
 }
@@ -1358,9 +1394,13 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_idct_csc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    e = cudaFuncSetAttribute(k_idct_csc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_idct_csc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    e = cudaFuncSetAttribute(k_idct_csc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_idct_csc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_idct_csc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
 }
 
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
@@ -1405,10 +1445,10 @@ void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.tile1 - r.tile0;
     if (n == 0) return;
-    if (a.use_tma)
-        k_idct_csc<true><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status);
-    else
-        k_idct_csc<false><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status);
+#define B2J_IDCT_LAUNCH(T, Q) k_idct_csc<T, Q><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status)
+    if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false); else B2J_IDCT_LAUNCH(true, true); }
+    else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false); else B2J_IDCT_LAUNCH(false, true); }
+#undef B2J_IDCT_LAUNCH
 }
 
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s)

@@ -38,6 +38,7 @@ struct DecodeArgs
     // sizes
     uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len;
     bool use_tma;
+    bool any_wide_q;         // some quantiser of the batch exceeds 255 (16-bit DQT): generic dequantisation
     uint32_t huff_variant;   // bit 0: 128-bit stream prefetch, bit 1: deferred coefficient store
 };
 

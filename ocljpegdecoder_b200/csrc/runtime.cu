@@ -519,6 +519,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.n_tiles = (uint32_t)tiles.size();
     a.max_lut_len = max_lut_len;
     a.use_tma = ctx->use_tma;
+    a.any_wide_q = false;
+    for (const ImgDev &im : b->imgs) a.any_wide_q = a.any_wide_q || im.wide_q != 0;
     {
         const char *hv = getenv("B2J_HUFF_VARIANT");
         a.huff_variant = hv ? (uint32_t)atoi(hv) : 0u;

@@ -127,7 +127,7 @@ def _seg(marker, payload):
 
 
 def build_jpeg(width, height, sampling, blocks, qtabs, restart_interval=0, fill_before_rst=0,
-               tables=None, comp_tables=((0, 0), (1, 1), (1, 1)), with_app0=True, trailing=b""):
+               tables=None, comp_tables=((0, 0), (1, 1), (1, 1)), with_app0=True, trailing=b"", dqt16=False):
     """sampling: luma (h, v) with 1x1 chroma. blocks: int array [n_blocks, 64] in MCU order and
     SCAN (zig-zag) coefficient order, blocks[:,0] = absolute DC. qtabs: two 64-lists (zig-zag order)
     for luma and chroma. tables: dict like STD_TABLES. Returns the file bytes."""
@@ -142,8 +142,12 @@ def build_jpeg(width, height, sampling, blocks, qtabs, restart_interval=0, fill_
     out = bytearray(b"\xFF\xD8")
     if with_app0:
         out += _seg(0xE0, b"JFIF\x00\x01\x01\x00\x00\x01\x00\x01\x00\x00")
-    out += _seg(0xDB, bytes([0]) + bytes(qtabs[0]))
-    out += _seg(0xDB, bytes([1]) + bytes(qtabs[1]))
+    if dqt16:   # precision 1: 64 big-endian 16-bit entries (the reference reads them WITHOUT a byte swap, parser.cpp:81-87)
+        out += _seg(0xDB, bytes([0x10]) + b"".join(int(q).to_bytes(2, "big") for q in qtabs[0]))
+        out += _seg(0xDB, bytes([0x11]) + b"".join(int(q).to_bytes(2, "big") for q in qtabs[1]))
+    else:
+        out += _seg(0xDB, bytes([0]) + bytes(qtabs[0]))
+        out += _seg(0xDB, bytes([1]) + bytes(qtabs[1]))
     sof = bytes([8]) + height.to_bytes(2, "big") + width.to_bytes(2, "big") + bytes([3])
     sof += bytes([1, (h << 4) | v, 0, 2, 0x11, 1, 3, 0x11, 1])
     out += _seg(0xC0, sof)

@@ -311,3 +311,23 @@ def test_selfsync_corrupt_streams_are_flagged(decoder, oracle):
         rc, *_ = oracle.decode(cases[n], want_pixels=False)
         if rc != 0:
             assert s != 0, "%s: the reference path fails but the GPU status is clean" % n
+
+
+def test_sixteen_bit_quantisation_tables(decoder, oracle, reference=None):
+    """DQT with 16-bit precision: the reference keeps the raw little-endian words (no byte swap), so the
+    quantisers exceed 255 and the kernel's generic (non-dp2a) dequantisation runs. Mixed with 8-bit images."""
+    rng = np.random.RandomState(3)
+    blocks = np.zeros((2 * 6, 64), np.int64)
+    blocks[:, 0] = rng.randint(-20, 20, 12)
+    blocks[:, 1:4] = rng.randint(-2, 3, (12, 3))
+    q16 = [[(1 + (i % 3)) for i in range(64)], [2] * 64]      # big-endian 0x0001.. -> read as 0x0100.. = 256..768
+    f16 = jpegcraft.build_jpeg(32, 16, (2, 2), blocks, q16, dqt16=True)
+    f8 = synth.synth_jpeg(64, 48, 1, 80, "420", 2)
+    st, coefs, pix = _decode(decoder, [f16, f8])
+    assert not st.any()
+    for f, c, p in zip([f16, f8], coefs, pix):
+        rc, img, coef, bgra = oracle.decode(f)
+        assert rc == 0
+        assert np.array_equal(c, coef)
+        _check_pixels(p, bgra)
+    assert np.abs(coefs[0]).max() >= 256
