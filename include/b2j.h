@@ -68,6 +68,11 @@ extern "C" {
 /* ---- accept gate ---- */
 #define B2J_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: 4:2:0 (22,11,11) and 4:4:4        */
 #define B2J_GATE_EXTENDED 1  /* + 4:2:2 (21,11,11) and 4:4:0 (12,11,11), BASELINE config 4   */
+/* OR-able with either gate (real-world files): tolerate what load_jpg() chokes on
+ * -- COM / APPn / other length-prefixed segments anywhere before SOS are skipped (parser.cpp:410-412
+ * stops at them), fill FFs before a marker are skipped, tables may be redefined, 16-bit DQT entries are
+ * read big-endian as the standard says (parser.cpp:81-87 does not swap). */
+#define B2J_PARSE_ROBUST 2
 
 /* reference enum ColorSpace (macro.h:114-119) */
 #define B2J_CS_YUV444 0

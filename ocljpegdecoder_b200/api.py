@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 GATE_REFERENCE = 0
 GATE_EXTENDED = 1
+PARSE_ROBUST = 2     # OR-able: skip COM / late APPn / unknown segments, big-endian 16-bit DQT
 
 B2J_OK = 0
 B2J_E_NODEVICE = -7

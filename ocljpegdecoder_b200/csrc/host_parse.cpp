@@ -30,19 +30,20 @@ struct Reader
 inline unsigned be16(const uint8_t *b) { return ((unsigned)b[0] << 8) | b[1]; }
 
 // parser.cpp:47-100
-bool parse_dqt(b2j_image_desc &d, Reader &r, size_t len)
+bool parse_dqt(b2j_image_desc &d, Reader &r, size_t len, bool robust)
 {
     while (len > 0)
     {
         uint8_t head, raw[128];
         if (!r.take(&head, 1)) return false;
         const int prec = head >> 4, id = head & 0xF;
-        if (id > 3 || d.quant_present[id] || prec > 1) return false;
+        if (id > 3 || (d.quant_present[id] && !robust) || prec > 1) return false;   // robust: a later DQT redefines the slot
         const size_t body = prec ? 128 : 64;
         if (!r.take(raw, body)) return false;
         for (int i = 0; i < 64; i++)
-            d.quant[id][i] = prec ? (uint16_t)(raw[2 * i] | (raw[2 * i + 1] << 8))   // no byte swap: parser.cpp:81-87
-                                  : raw[i];
+            d.quant[id][i] = !prec ? raw[i]
+                             : robust ? (uint16_t)((raw[2 * i] << 8) | raw[2 * i + 1])     // big-endian, ITU T.81 B.2.4.1
+                                      : (uint16_t)(raw[2 * i] | (raw[2 * i + 1] << 8));    // no byte swap: parser.cpp:81-87
         d.quant_present[id] = 1;
         if (len < body + 1) return false;
         len -= body + 1;
@@ -67,7 +68,7 @@ bool parse_sof0(b2j_image_desc &d, Reader &r, size_t len)
 }
 
 // parser.cpp:170-270
-bool parse_dht(b2j_image_desc &d, Reader &r, size_t len)
+bool parse_dht(b2j_image_desc &d, Reader &r, size_t len, bool robust)
 {
     while (len > 0)
     {
@@ -76,8 +77,9 @@ bool parse_dht(b2j_image_desc &d, Reader &r, size_t len)
         const int tc = head >> 4, th = head & 0xF;
         if (tc > 1 || th > 3) return false;
         const int slot = tc * 4 + th;
-        if (d.huff_present[slot]) return false;
+        if (d.huff_present[slot] && !robust) return false;
         if (!r.take(counts, 16)) return false;
+        memset(d.huff_counts[slot], 0, 16);
         unsigned total = 0, code = 0;
         for (int l = 1; l <= 16; l++)
         {
@@ -148,9 +150,11 @@ void derive_geometry(b2j_image_desc &d)
 
 } // namespace
 
-extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate, b2j_image_desc *out)
+extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate_flags, b2j_image_desc *out)
 {
     if (!file || !out) return B2J_E_ARG;
+    const bool robust = (gate_flags & B2J_PARSE_ROBUST) != 0;
+    const int gate = gate_flags & 1;
     b2j_image_desc &d = *out;
     memset(&d, 0, sizeof(d));
     Reader r{file, len, 0};
@@ -167,13 +171,34 @@ extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate, b2j_i
     }
     while (tag[1] != 0)
     {
+        if (robust)
+        {
+            // resynchronise on FF, skip fill bytes, stand-alone markers and anything length-prefixed we do not need
+            while (tag[0] != 0xFF || tag[1] == 0xFF || tag[1] == 0x00)
+            {
+                tag[0] = tag[1];
+                if (!r.take(&tag[1], 1)) return B2J_E_FORMAT;
+            }
+            const uint8_t m = tag[1];
+            const bool needed = m == 0xDB || m == 0xC0 || m == 0xC4 || m == 0xDD || m == 0xDA;
+            if (m == 0xD9) return B2J_E_FORMAT;
+            if ((m >= 0xC1 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) return B2J_E_UNSUPPORTED;   // not baseline
+            if (!needed)
+            {
+                if ((m >= 0xD0 && m <= 0xD7) || m == 0x01) { if (!r.take(tag, 2)) return B2J_E_FORMAT; continue; }
+                if (!r.take(lb, 2)) return B2J_E_FORMAT;
+                const size_t l = be16(lb);
+                if (l < 2 || !r.take(nullptr, l - 2) || !r.take(tag, 2)) return B2J_E_FORMAT;
+                continue;
+            }
+        }
         if (!r.take(lb, 2)) return B2J_E_FORMAT;
         const size_t seglen = (uint16_t)(be16(lb) - 2);
         switch (tag[1])
         {
-        case 0xDB: if (!parse_dqt(d, r, seglen)) return B2J_E_FORMAT; break;
+        case 0xDB: if (!parse_dqt(d, r, seglen, robust)) return B2J_E_FORMAT; break;
         case 0xC0: if (!parse_sof0(d, r, seglen)) return B2J_E_FORMAT; break;
-        case 0xC4: if (!parse_dht(d, r, seglen)) return B2J_E_FORMAT; break;
+        case 0xC4: if (!parse_dht(d, r, seglen, robust)) return B2J_E_FORMAT; break;
         case 0xDD:
             if (seglen != 2 || !r.take(lb, 2)) return B2J_E_FORMAT;   // parser.cpp:156-168
             d.restart_interval = (int32_t)be16(lb);

@@ -80,3 +80,30 @@ def test_no_device_no_fallback(built):
     with pytest.raises(b2j.B2JError) as ei:
         b2j.Decoder(0)
     assert ei.value.code == -7   # B2J_E_NODEVICE: the product path fails loudly without the device
+
+
+def test_robust_parse_mode_accepts_what_the_reference_parser_chokes_on(built, oracle, fixture_jpeg):
+    """COM / late APPn segments end the reference's parsing (parser.cpp:410-412).
+    With B2J_PARSE_ROBUST they are skipped and the header equals that of the clean file."""
+    import ocljpegdecoder_b200 as b2j
+    base = synth.synth_jpeg(96, 64, 77, 85, "420", 4)
+    rc0, d0 = b2j.parse_header(base, b2j.GATE_REFERENCE)
+    assert rc0 == 0
+    com = b"\xff\xfe" + (2 + 11).to_bytes(2, "big") + b"hello world"
+    app1 = b"\xff\xe1" + (2 + 6).to_bytes(2, "big") + b"Exif\x00\x00"
+    k = base.index(b"\xff\xdb")                      # in front of the first DQT
+    k2 = base.index(b"\xff\xc4")                     # in front of the first DHT
+    dirty = base[:k] + com + base[k:k2] + app1 + b"\xff" + base[k2:]     # + one fill byte before a marker
+    assert b2j.parse_header(dirty, b2j.GATE_REFERENCE)[0] != 0 and oracle.parse(dirty, 0)[0] != 0
+    rc, d = b2j.parse_header(dirty, b2j.GATE_REFERENCE | b2j.PARSE_ROBUST)
+    assert rc == 0
+    extra = len(dirty) - len(base)
+    assert (d.width, d.height, d.blk_count, d.restart_interval) == (d0.width, d0.height, d0.blk_count, d0.restart_interval)
+    assert d.scan_offset == d0.scan_offset + extra and d.scan_size == d0.scan_size
+    assert bytes(d.huff_counts) == bytes(d0.huff_counts) and bytes(d.quant) == bytes(d0.quant)
+    # robust mode is a superset: clean files parse identically
+    rc1, d1 = b2j.parse_header(base, b2j.GATE_EXTENDED | b2j.PARSE_ROBUST)
+    assert rc1 == 0 and bytes(d1.huff_symbols) == bytes(d0.huff_symbols) and d1.scan_offset == d0.scan_offset
+    assert b2j.parse_header(fixture_jpeg, b2j.PARSE_ROBUST)[0] == 0
+    # progressive stays rejected
+    assert b2j.parse_header(base.replace(b"\xff\xc0", b"\xff\xc2", 1), b2j.PARSE_ROBUST)[0] != 0

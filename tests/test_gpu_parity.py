@@ -331,3 +331,20 @@ def test_sixteen_bit_quantisation_tables(decoder, oracle, reference=None):
         assert np.array_equal(c, coef)
         _check_pixels(p, bgra)
     assert np.abs(coefs[0]).max() >= 256
+
+
+def test_robust_mode_decodes_files_with_comments(decoder, oracle):
+    """A COM segment (Pillow's comment=) and an extra APP1 make the reference parser stop; in robust mode the
+    decode equals the decode of the same image written without them."""
+    import ocljpegdecoder_b200 as b2j
+    base = synth.synth_jpeg(160, 96, 31, 88, "420", 4)
+    com = b"\xff\xfe" + (2 + 7).to_bytes(2, "big") + b"comment"
+    k = base.index(b"\xff\xdb")
+    dirty = base[:k] + com + base[k:]
+    assert oracle.parse(dirty, 1)[0] != 0
+    outs, st = decoder.decode_host([dirty, base], gate=b2j.GATE_EXTENDED | b2j.PARSE_ROBUST)
+    assert not st.any()
+    rc, _, _, bgra = oracle.decode(base)
+    assert rc == 0
+    _check_pixels(outs[0], bgra)
+    _check_pixels(outs[1], bgra)
