@@ -64,6 +64,7 @@ extern "C" {
 #define B2J_ST_BLOCK_OVERFLOW 0x08 /* more than 64 coefficients in a block (decoder.cpp:259) */
 #define B2J_ST_DC_RANGE 0x10      /* DC category > 16 or DC predictor outside int16          */
 #define B2J_ST_SEGMENT_END 0x20   /* a restart interval did not end at its marker            */
+#define B2J_ST_INTERNAL 0x4000    /* a TMA tile load did not complete (never observed; guards against a hang) */
 
 /* ---- accept gate ---- */
 #define B2J_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: 4:2:0 (22,11,11) and 4:4:4        */

@@ -422,6 +422,7 @@ struct BitReader
         bitpos = a * 8u;
         nref = 0u;
     }
+    __device__ __forceinline__ uint32_t words_consumed() const { return nref; }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
     __device__ __forceinline__ void refill()
     {
@@ -460,6 +461,68 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
 }
 
+// Bit reader whose stream arrives through a per-lane ring in shared memory filled by cp.async (LDGSTS):
+// 2 x 16 bytes per lane; the chunk behind the one being read is requested when the reader enters a
+// chunk, i.e. four window shifts (>= 128 bits, some twenty symbols) before its first word is needed,
+// and the copy never occupies a register. Every global sector is fetched once (16 bytes per request)
+// instead of once per 4-byte word as with plain loads, which miss L1 here: at 25 warps per SM the
+// streams of 896 lanes do not fit in the ~32 KB of L1 that the shared-memory carve-out leaves.
+struct RingReader
+{
+    uint32_t cur, nxt;     // big-endian words: `cur` holds the bit at `bitpos`
+    uint32_t bitpos;       // 0..31 after refill()
+    uint32_t w4;           // 4 * index of the next stream word to enter the window (from the 16-byte aligned base)
+    uint32_t w4_0;         // its value after init(): consumed words = (w4 - w4_0) / 4
+    uint32_t ring;         // shared address of this lane's 32-byte ring
+    const uint8_t *gbase;  // 16-byte aligned global address of stream word 0
+
+    __device__ __forceinline__ void fetch(uint32_t chunk)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + ((chunk & 1u) << 4)), "l"(gbase + (size_t)chunk * 16u) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t byte_index) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (byte_index & 28u)) : "memory");
+        return __byte_perm(v, 0, 0x0123);
+    }
+    __device__ __forceinline__ void init(const uint8_t *p, uint32_t ring_addr)
+    {
+        const uint32_t a16 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+        gbase = p - a16;
+        ring = ring_addr;
+        fetch(0);
+        fetch(1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint32_t ws = a16 & 12u;       // byte index of the word that holds p
+        cur = word(ws);
+        nxt = word(ws + 4u);
+        w4 = ws + 8u;
+        if (w4 >= 16u) { fetch(2); asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // chunk 0 is already used up
+        w4_0 = w4;
+        bitpos = (a16 & 3u) * 8u;
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
+    __device__ __forceinline__ void refill()
+    {
+        if (bitpos >= 32u)
+        {
+            cur = nxt;
+            nxt = word(w4);
+            w4 += 4u;
+            bitpos -= 32u;
+            if ((w4 & 12u) == 0u)
+            {
+                // entering chunk w4/16: the chunk behind it goes into the slot just drained; all older copies have landed
+                fetch((w4 >> 4) + 1u);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
+        }
+    }
+    __device__ __forceinline__ uint32_t words_consumed() const { return (w4 - w4_0) >> 2; }
+};
+
 // One symbol from a two-level LUT in shared memory (entry format: b2j_internal.h). `tab` is the
 // shared-window byte address of the table. Returns the leaf entry, 0 when no codeword matches.
 __device__ __forceinline__ uint32_t lut_first(uint32_t tab, uint32_t pk)
@@ -492,6 +555,9 @@ __device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
 // SYNC = true : a lane is a sub-sequence of a stream without restart markers; its first block, bit
 //   position, MCU phase, block index and DC predictors come from the self-synchronisation passes
 //   (SubRec / SubPre), and the table choice is per lane.
+template <bool RING> struct ReaderOf { typedef BitReader<1> type; };
+template <> struct ReaderOf<true> { typedef RingReader type; };
+
 template <bool WIDE, bool DEFER, bool SYNC>
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
@@ -503,7 +569,8 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     // [ per-lane block slots: kHuffThreads * 128 B ][ zig-zag byte offsets: 64 B ][ LUT set ]
     uint8_t *s_slots = smem;
     uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + 64);
+    constexpr uint32_t kRingBytes = WIDE ? kHuffThreads * 32 : 0;   // [ ... ][ per-lane stream rings ][ LUT set ]
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + 64 + kRingBytes);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -566,9 +633,10 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         decodable = active && nblk > 0;
     }
 
-    BitReader<WIDE ? 2 : 1> br;
+    typename ReaderOf<WIDE>::type br;
     const uint8_t *base = clean + im.raw_off;
-    br.init(base + (decodable ? start : 0u));
+    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + 64 + tid * 32u);
+    else reinterpret_cast<BitReader<1> &>(br).init(base + (decodable ? start : 0u));
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
     if (SYNC) br.bitpos += start_bit & 7u;
     bool dead = !decodable;
@@ -576,7 +644,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint32_t sm_base;   // kept opaque: otherwise the shared-window base is re-derived (S2R) inside the decode loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_addr(smem)));
     const uint32_t sm_zz = sm_base + kHuffThreads * 128;
-    const uint32_t sm_lut = sm_zz + 64;
+    const uint32_t sm_lut = sm_zz + 64 + kRingBytes;
     // shared address of this lane's slot with the chunk swizzle folded in: coefficient n lives at
     // slot + ((n>>3) ^ (lane&7))*16 + (n&7)*2 == slot_key ^ (2n)   (slots are 128-byte aligned)
     const uint32_t slot_key = sm_base + tid * 128u + ((lane & 7u) << 4);
@@ -675,7 +743,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         // bits consumed since `start`; a restart interval must end exactly at its marker
         // (decoder.cpp:296-302 aligns to the byte boundary and expects RSTn there)
-        const uint64_t bits = (uint64_t)br.nref * 32u + br.bitpos - bit0;
+        const uint64_t bits = (uint64_t)br.words_consumed() * 32u + br.bitpos - bit0;
         const uint64_t used = (bits + 7u) >> 3;
         const uint64_t avail = (uint64_t)end - start;
         if (used > avail) err |= B2J_ST_OVERRUN;
@@ -1379,14 +1447,14 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
 
 // =====================================================================================
 // Launchers (host).
-size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128 + 64 + (size_t)max_lut_len * 2; }
+size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + 64 + (ring ? (size_t)kHuffThreads * 32 : 0) + (size_t)max_lut_len * 2; }
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {
-    const int hb = (int)huff_smem_bytes(max_lut_len);
+    const int hb = (int)huff_smem_bytes(max_lut_len, true);
     cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
+    e = cudaFuncSetAttribute(k_huff_decode<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_huff_decode<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
@@ -1418,9 +1486,9 @@ void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.cta1 - r.cta0;
     if (n == 0) return;
-    const size_t sm = huff_smem_bytes(a.max_lut_len);
-    if (a.huff_variant & 2u)
-        k_huff_decode<false, true, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
+    const size_t sm = huff_smem_bytes(a.max_lut_len, false);
+    if (a.huff_variant & 1u)
+        k_huff_decode<true, false, false><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len, true), s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
                                                                     a.coef, a.status, nullptr, nullptr);
     else
         k_huff_decode<false, false, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
@@ -1437,7 +1505,7 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
         k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_stats);
     k_sync_sweep<<<ni, 32, lut_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.stamps, (uint32_t)kSyncRounds, a.sync_stats);
     k_sync_scan<<<ni, 256, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.recs, a.pres);
-    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
+    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
                                                                                            a.clean_len, a.luts, a.coef, a.status, a.recs, a.pres);
 }
 

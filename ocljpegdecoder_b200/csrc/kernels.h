@@ -47,7 +47,7 @@ struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
-size_t huff_smem_bytes(uint32_t max_lut_len);
+size_t huff_smem_bytes(uint32_t max_lut_len, bool ring);
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
 void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // kSyncRounds + 4 kernels
