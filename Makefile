@@ -45,3 +45,9 @@ clean:
 	$(MAKE) -s -C oracle clean
 
 .PHONY: all oracle clean mathcheck
+
+# measurement variants: make variant NAME=x DEFS="-DB2J_...=..." -> build/var_x/libb2j.so (load with B2J_LIBRARY=...)
+variant:
+	@mkdir -p build/var_$(NAME)
+	$(NVCC) $(NVFLAGS) $(DEFS) -c $(CSRC)/kernels.cu -o build/var_$(NAME)/kernels.o 2> build/var_$(NAME)/kernels.ptxas.log
+	$(NVCC) $(ARCH) -shared -o build/var_$(NAME)/libb2j.so build/var_$(NAME)/kernels.o $(OBJDIR)/runtime.o $(OBJDIR)/host_parse.o $(OBJDIR)/huff_lut.o

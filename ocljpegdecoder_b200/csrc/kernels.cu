@@ -395,6 +395,272 @@ k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, co
     }
 }
 
+// ---- single-pass variant: count, prefix across the chunks of an image and write in ONE kernel.
+// Every chunk publishes a 64-bit state word: first its own totals ("aggregate"), later the totals of the
+// image up to and including itself ("inclusive"). A chunk obtains its base by looking back over its
+// predecessors' words (decoupled look-back: aggregates are added until an inclusive word is met), so no
+// chunk waits for more than the local counting of the chunks in front of it, and the bytes are classified
+// once instead of twice. CTAs of a grid start in blockIdx order, so a predecessor is always resident or done.
+// The word carries everything a successor needs, so relaxed accesses suffice (no fences):
+//   bits 63:62 flag (0 empty, 1 aggregate, 2 inclusive) | bit 61 a terminator was met | 60:32 markers | 31:0 kept bytes
+// The look-back latency hides behind the compaction: the kept bytes are squeezed into shared memory at their
+// CHUNK-LOCAL offsets (which need no base), warp 0 probes its predecessors before it starts squeezing and
+// evaluates the probe afterwards; only the copy-out (shifted to the alignment of the global destination)
+// and the restart-interval table wait for the base.
+constexpr uint64_t kStAgg = 1ull << 62, kStIncl = 2ull << 62, kStTerm = 1ull << 61;
+__device__ __forceinline__ uint64_t st_pack(uint64_t flag, uint32_t keep, uint32_t mark, bool term)
+{
+    return flag | (term ? kStTerm : 0ull) | ((uint64_t)mark << 32) | keep;
+}
+__device__ __forceinline__ uint64_t st_load(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_store(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Phase A of a 16-byte group: squeeze the dropped bytes out of the registers and store the kept ones to
+// shared memory at byte offset o (single bytes up to the next word boundary, whole words, tail bytes).
+__device__ __forceinline__ void squeeze_group(uint8_t *__restrict__ s_out, uint32_t o, const uint32_t w[4], const ScanFlags &f, uint32_t nkeep)
+{
+    uint32_t B[4] = {w[0], w[1], w[2], w[3]};
+    if (nkeep != 16u)
+    {
+        uint32_t keep16 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) keep16 |= ((((f.keep[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+        // highest dropped byte first (bytes above the last kept one need no move)
+        const uint32_t span = keep16 ? 32u - (uint32_t)__clz(keep16) : 0u;
+        uint32_t drop = ~keep16 & ((1u << span) - 1u);
+        while (drop)
+        {
+            const uint32_t j = 31u - (uint32_t)__clz(drop);
+            drop ^= 1u << j;
+            const uint32_t wi = j >> 2, lm = (1u << (8u * (j & 3u))) - 1u;
+            const uint32_t sh0 = __funnelshift_r(B[0], B[1], 8), sh1 = __funnelshift_r(B[1], B[2], 8),
+                           sh2 = __funnelshift_r(B[2], B[3], 8), sh3 = B[3] >> 8;
+            B[0] = wi == 0u ? ((B[0] & lm) | (sh0 & ~lm)) : B[0];
+            B[1] = wi == 1u ? ((B[1] & lm) | (sh1 & ~lm)) : (wi < 1u ? sh1 : B[1]);
+            B[2] = wi == 2u ? ((B[2] & lm) | (sh2 & ~lm)) : (wi < 2u ? sh2 : B[2]);
+            B[3] = wi == 3u ? ((B[3] & lm) | (sh3 & ~lm)) : sh3;
+        }
+    }
+    uint32_t n = nkeep;
+    const uint32_t head = min((4u - (o & 3u)) & 3u, n);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if ((uint32_t)k < head) s_out[o + k] = (uint8_t)(B[0] >> (8 * k));
+    if (head)
+    {
+        const uint32_t hs = head * 8u;   // drop the head bytes from the register array
+        B[0] = __funnelshift_r(B[0], B[1], hs);
+        B[1] = __funnelshift_r(B[1], B[2], hs);
+        B[2] = __funnelshift_r(B[2], B[3], hs);
+        B[3] = B[3] >> hs;
+    }
+    o += head; n -= head;
+    uint32_t *wo = reinterpret_cast<uint32_t *>(s_out + o);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if ((uint32_t)(4 * k + 4) <= n) wo[k] = B[k];
+    const uint32_t full = n >> 2, tail = n & 3u;
+    const uint32_t tw = full == 0u ? B[0] : (full == 1u ? B[1] : (full == 2u ? B[2] : B[3]));
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if ((uint32_t)k < tail) s_out[o + full * 4u + k] = (uint8_t)(tw >> (8 * k));
+}
+
+// Phase B of a 16-byte group: the restart-interval starts of its RSTn markers (clean_pos = position of the
+// group's first kept byte in the image's clean stream, rank = ordinal of the next marker of the image).
+__device__ __forceinline__ void mark_group(const uint32_t w[4], const ScanFlags &f, uint32_t &rank, uint32_t clean_pos, const ImgDev &im,
+                                           uint32_t img_idx, uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
+{
+    if (!(f.mark[0] | f.mark[1] | f.mark[2] | f.mark[3])) return;
+    uint32_t keep16 = 0, mark16 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        keep16 |= ((((f.keep[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+        mark16 |= ((((f.mark[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
+    }
+    while (mark16)
+    {
+        const uint32_t j = (uint32_t)__ffs(mark16) - 1u;
+        mark16 &= mark16 - 1u;
+        if (im.has_dri && rank + 1 < im.n_segs)
+        {
+            seg_start[im.seg_first + rank + 1] = clean_pos + __popc(keep16 & ((1u << j) - 1u));
+            const uint32_t wj = j < 4u ? w[0] : (j < 8u ? w[1] : (j < 12u ? w[2] : w[3]));
+            const uint32_t bj = (wj >> (8 * (j & 3u))) & 0xFFu;
+            if (bj != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
+        }
+        rank++;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads, 3)
+k_unstuff_fused(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
+                const uint32_t *__restrict__ chunk_img, uint64_t *__restrict__ chunk_state, uint32_t *__restrict__ clean_len,
+                uint32_t *__restrict__ seg_start, int32_t *__restrict__ status, uint32_t chunk0)
+{
+    __shared__ uint32_t s_min;
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_base[3];   // kept bytes / markers in front of this chunk, dead flag
+    __shared__ __align__(16) uint8_t s_out[kScanChunkBytes + 32];
+    const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t img_idx = chunk_img[c];
+    const ImgDev &im = imgs[img_idx];
+    const uint32_t k = c - im.chunk_first;   // chunk index inside the image
+    const uint32_t pos = k * kScanChunkBytes + tid * (16u * kScanGroups);
+    ScanThread st;
+    st.load_classify(raw + im.raw_off, pos);
+    // the scan ends in one chunk per image: only there is the position of the terminator worked out
+    uint32_t term = kNoTerm;
+    {
+        uint32_t any = 0;
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++) any |= st.f[g].term[0] | st.f[g].term[1] | st.f[g].term[2] | st.f[g].term[3];
+        if (__syncthreads_or(any != 0u))
+        {
+            term = block_first_term(st.first_term(), tid, &s_min);
+            st.cut(local_limit(term, tid));
+        }
+    }
+    uint32_t nkeep[kScanGroups], mine = 0;
+#pragma unroll
+    for (int g = 0; g < kScanGroups; g++)
+    {
+        nkeep[g] = __popc(squeeze(st.f[g].keep));
+        mine += nkeep[g] | (__popc(squeeze(st.f[g].mark)) << 16);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += a;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w8 = 0; w8 < kScanThreads / 32; w8++)
+    {
+        const uint32_t v = s_warp[w8];
+        before += (w8 < (int)warp) ? v : 0u;
+        total += v;
+    }
+    const uint32_t own_keep = total & 0xFFFFu, own_mark = total >> 16;
+    const bool own_term = term != kNoTerm;
+    const uint32_t excl = before + incl - mine;
+
+    // warp 0: publish the aggregate, probe the (up to 32) nearest predecessors; evaluated after the squeeze
+    uint64_t probe = kStIncl;   // in front of the image: an inclusive zero
+    const uint64_t *probe_p = chunk_state + (c - k) + (k - 1u - lane);
+    if (warp == 0 && k != 0)
+    {
+        if (lane == 0) st_store(chunk_state + c, st_pack(kStAgg, own_keep, own_mark, own_term));
+        if (lane < k) probe = st_load(probe_p);
+    }
+
+    // phase A: squeeze the kept bytes into shared memory at their chunk-local offsets
+    {
+        uint32_t lo = excl & 0xFFFFu;
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++)
+        {
+            squeeze_group(s_out, lo, st.w[g], st.f[g], nkeep[g]);
+            lo += nkeep[g];
+        }
+    }
+
+    if (warp == 0)
+    {
+        uint32_t bk = 0, bm = 0;
+        bool dead = false;
+        if (k != 0)
+        {
+            uint32_t j = k;   // predecessors k-1 .. 0 are still to be accounted for
+            uint64_t w = probe;
+            while (true)
+            {
+                if (lane < j) { while ((w >> 62) == 0ull) w = st_load(probe_p); }
+                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2ull);
+                const uint32_t upto = inc ? (uint32_t)__ffs(inc) - 1u : 31u;   // nearest inclusive word (lane order = distance)
+                uint32_t kk = lane <= upto ? (uint32_t)w : 0u;
+                uint32_t mm = lane <= upto ? (uint32_t)(w >> 32) & 0x1FFFFFFFu : 0u;
+                const bool tt = lane <= upto && (w & kStTerm);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { kk += __shfl_xor_sync(0xFFFFFFFFu, kk, o); mm += __shfl_xor_sync(0xFFFFFFFFu, mm, o); }
+                bk += kk; bm += mm;
+                dead = dead || __any_sync(0xFFFFFFFFu, tt);
+                if (inc) break;
+                j -= 32u;
+                probe_p -= 32;
+                w = lane < j ? st_load(probe_p) : kStIncl;
+            }
+        }
+        if (lane == 0)
+        {
+            // a chunk behind the end of the scan contributes nothing
+            st_store(chunk_state + c, dead ? st_pack(kStIncl, bk, bm, true) : st_pack(kStIncl, bk + own_keep, bm + own_mark, own_term));
+            s_base[0] = bk; s_base[1] = bm; s_base[2] = dead ? 1u : 0u;
+            if (k == 0) seg_start[im.seg_first] = 0;
+            if (!dead && (own_term || k + 1u == im.n_chunks))
+            {
+                // this chunk ends the scan: totals of the image
+                clean_len[img_idx] = bk + own_keep;
+                // a missing RSTn makes the reference fail with "expected RSTn" (decoder.cpp:298-302)
+                if (im.has_dri && bm + own_mark + 1u < im.n_segs) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);
+            }
+        }
+    }
+    __syncthreads();
+    if (s_base[2]) return;   // behind the end of the scan (uniform for the CTA)
+    const uint32_t base_keep = s_base[0];
+
+    // phase B: restart-interval table
+    {
+        uint32_t lo = excl & 0xFFFFu;
+        uint32_t rank = s_base[1] + (excl >> 16);   // ordinal of the next RSTn in the image
+#pragma unroll
+        for (int g = 0; g < kScanGroups; g++)
+        {
+            mark_group(st.w[g], st.f[g], rank, base_keep + lo, im, img_idx, seg_start, status);
+            lo += nkeep[g];
+        }
+    }
+    // copy out: shared byte i goes to clean[g0 + i]. 16-byte vectors at aligned global addresses, assembled
+    // from five shared words shifted by the (CTA-uniform) misalignment; single bytes at the two ragged ends.
+    const uint64_t g0 = im.raw_off + base_keep;
+    const uint32_t a = (uint32_t)(g0 & 15u);
+    uint8_t *gd = clean + (g0 - a);                 // aligned; global byte gd[x] <- shared byte x - a
+    const uint32_t end = a + own_keep;
+    const uint32_t sh = ((4u - (a & 3u)) & 3u) * 8u;
+    for (uint32_t v = tid; v * 16u < end; v += kScanThreads)
+    {
+        const uint32_t lo16 = v * 16u;
+        if (lo16 >= a && lo16 + 16u <= end)
+        {
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_out) + ((lo16 - a) >> 2);
+            const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4];
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+            *reinterpret_cast<uint4 *>(gd + lo16) = o;
+        }
+        else
+        {
+            const uint32_t from = lo16 < a ? a : lo16, to = lo16 + 16u < end ? lo16 + 16u : end;
+            for (uint32_t q = from; q < to; q++) gd[q] = s_out[q - a];
+        }
+    }
+}
+
 // =====================================================================================
 // Huffman decode.
 // Per-lane bit reader over the clean stream: a 64-bit big-endian window (cur:nxt) and DEPTH raw words
@@ -1475,6 +1741,11 @@ void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t nc = r.chunk1 - r.chunk0, ni = r.img1 - r.img0;
     if (nc == 0 || ni == 0) return;
+    if (a.prepass_fused)
+    {
+        k_unstuff_fused<<<nc, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_state, a.clean_len, a.seg_start, a.status, r.chunk0);
+        return;
+    }
     k_scan_count<<<nc, kScanThreads, 0, s>>>(a.raw, a.imgs, a.chunk_img, a.chunk_cnt, a.chunk_term, r.chunk0);
     k_scan_chunks<<<(ni + 3) / 4, 128, 0, s>>>(a.imgs, (int)r.img0, (int)r.img1, a.chunk_cnt, a.chunk_term, a.chunk_base_keep,
                                                a.chunk_base_mark, a.clean_len, a.seg_start, a.status);

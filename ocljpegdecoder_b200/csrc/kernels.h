@@ -25,7 +25,8 @@ struct DecodeArgs
     const CUtensorMap *tmap;   // host copy, passed by value to the kernel
     // scratch
     uint8_t *clean;
-    uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;
+    uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;   // three-kernel pre-pass (B2J_PREPASS=3)
+    uint64_t *chunk_state;   // single-pass pre-pass: look-back words, zeroed before every decode
     uint32_t *clean_len, *seg_start;
     SubRec *recs;       // self-synchronising path: one record per sub-sequence
     SubPre *pres;
@@ -39,6 +40,7 @@ struct DecodeArgs
     uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len;
     bool use_tma;
     bool any_wide_q;         // some quantiser of the batch exceeds 255 (16-bit DQT): generic dequantisation
+    bool prepass_fused;      // single-pass pre-pass (default); B2J_PREPASS=3 selects the three-kernel one
     uint32_t huff_variant;   // bit 0: 128-bit stream prefetch, bit 1: deferred coefficient store
 };
 

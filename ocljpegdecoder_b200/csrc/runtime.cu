@@ -111,7 +111,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -305,7 +305,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         ImgDev &im = b->imgs[(size_t)i];
         memset(&im, 0, sizeof(im));
         if (d.width <= 0 || d.height <= 0 || d.mcu_count <= 0 || d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset ||
-            d.scan_size >= 0xFFFF0000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
+            d.scan_size >= 0x40000000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
         { rc = B2J_E_ARG; break; }
         img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
         img_scta0[(size_t)i] = (uint32_t)sctas.size(); img_simg0[(size_t)i] = (uint32_t)simgs.size();
@@ -446,6 +446,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_pres = place(sizeof(SubPre) * (size_t)sub_total);
     b->off_stamps = place(4 * (size_t)sub_total);
     b->off_sync_stats = place(4 * 8);
+    b->off_chunk_state = place(8 * chunk_img.size());
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
     b->coef_rows = blk_total + kTileBlocks;   // one tile of padding: the last tile may read past the last block
@@ -508,6 +509,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.chunk_term = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_term);
     a.chunk_base_keep = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bk);
     a.chunk_base_mark = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bm);
+    a.chunk_state = reinterpret_cast<uint64_t *>(b->d_scratch + b->off_chunk_state);
     a.clean_len = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_clean_len);
     a.seg_start = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_seg_start);
     a.status = reinterpret_cast<int32_t *>(b->d_scratch + b->off_status);
@@ -522,6 +524,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.any_wide_q = false;
     for (const ImgDev &im : b->imgs) a.any_wide_q = a.any_wide_q || im.wide_q != 0;
     {
+        const char *pp = getenv("B2J_PREPASS");
+        a.prepass_fused = !(pp && atoi(pp) == 3);
         const char *hv = getenv("B2J_HUFF_VARIANT");
         a.huff_variant = hv ? (uint32_t)atoi(hv) : 0u;
     }
@@ -529,7 +533,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b2j_batch_info &inf = b->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_images = n;
-    inf.kernel_launches = (int32_t)b->parts.size() * (4 + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
+    inf.kernel_launches = (int32_t)b->parts.size() * ((a.prepass_fused ? 1 : 3) + 1 + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
     inf.scan_bytes = scan_bytes;
@@ -594,6 +598,7 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
     CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
     CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
     CU_TRY(cudaMemsetAsync(a.sync_stats, 0, 4 * 8, s));
+    if (a.prepass_fused) CU_TRY(cudaMemsetAsync(a.chunk_state, 0, 8 * (size_t)a.n_chunks, s));
     const size_t np = b->parts.size();
     for (size_t p = 0; p < np; p++)
     {
