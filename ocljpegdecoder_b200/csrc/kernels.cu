@@ -674,21 +674,25 @@ struct BitReader
     uint32_t raw[DEPTH];   // look-ahead, memory byte order; raw[0] enters the window next
     uint32_t bitpos;       // 0..31 after refill()
     uint32_t nref;         // words shifted into the window since init()
-    const uint32_t *wp;    // next word to fetch
+    uint32_t wi;           // index (from wbase) of the next word to fetch: a fixed per-lane base and a 32-bit index
+    const uint32_t *wbase; // cost one IMAD.WIDE per fetch; a moving 64-bit pointer costs two more instructions
 
-    __device__ __forceinline__ void init(const uint8_t *p)
+    // stream: 4-byte aligned base of the image's stream; off: byte offset of the first byte to read
+    __device__ __forceinline__ void init(const uint8_t *stream, uint32_t off)
     {
-        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-        wp = reinterpret_cast<const uint32_t *>(p - a);
-        cur = __byte_perm(__ldg(wp), 0, 0x0123);
-        nxt = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+        wbase = reinterpret_cast<const uint32_t *>(stream) + (off >> 2);
+        cur = __byte_perm(__ldg(wbase), 0, 0x0123);
+        nxt = __byte_perm(__ldg(wbase + 1), 0, 0x0123);
 #pragma unroll
-        for (int k = 0; k < DEPTH; k++) raw[k] = __ldg(wp + 2 + k);
-        wp += 2 + DEPTH;
-        bitpos = a * 8u;
+        for (int k = 0; k < DEPTH; k++) raw[k] = __ldg(wbase + 2 + k);
+        wi = 2 + DEPTH;
+        bitpos = (off & 3u) * 8u;
         nref = 0u;
     }
+    // words shifted into the window since init(): nref, or the same number from the fetch index for loops
+    // that never read nref (its updates are then dead code)
     __device__ __forceinline__ uint32_t words_consumed() const { return nref; }
+    __device__ __forceinline__ uint32_t words_fetched() const { return wi - (2u + DEPTH); }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
     __device__ __forceinline__ void refill()
     {
@@ -698,8 +702,8 @@ struct BitReader
             nxt = __byte_perm(raw[0], 0, 0x0123);
 #pragma unroll
             for (int k = 0; k + 1 < DEPTH; k++) raw[k] = raw[k + 1];
-            raw[DEPTH - 1] = __ldg(wp);
-            wp++;
+            raw[DEPTH - 1] = __ldg(wbase + wi);
+            wi++;
             nref++;
             bitpos -= 32u;
         }
@@ -811,9 +815,9 @@ __device__ __forceinline__ uint32_t lut_second(uint32_t tab, uint32_t pk, uint32
 // s32 = 32 - bit count (32 -> no bits -> 0). A leading 1 bit means positive.
 __device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
 {
-    const uint32_t pos = (uint32_t)((int32_t)v >> 31);          // all ones when positive
-    const uint32_t mag = __funnelshift_rc(v ^ ~pos, 0u, s32);   // |value| (bits inverted when negative)
-    return (int32_t)((mag ^ ~pos) - ~pos);                      // negate when negative
+    const uint32_t u = __funnelshift_rc(v, 0u, s32);                 // the value bits as a number (no bits -> 0)
+    const uint32_t neg = (uint32_t)((int32_t)~v >> 31);              // all ones when the leading bit is 0
+    return (int32_t)(u - __funnelshift_rc(neg, 0u, s32));            // negative: u - (2^size - 1)
 }
 
 // SYNC = false: a lane is a restart interval (byte-aligned start from seg_start[], DC predictors 0, the
@@ -902,7 +906,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     typename ReaderOf<WIDE>::type br;
     const uint8_t *base = clean + im.raw_off;
     if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + 64 + tid * 32u);
-    else reinterpret_cast<BitReader<1> &>(br).init(base + (decodable ? start : 0u));
+    else reinterpret_cast<BitReader<1> &>(br).init(base, decodable ? start : 0u);
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
     if (SYNC) br.bitpos += start_bit & 7u;
     bool dead = !decodable;
@@ -1009,7 +1013,8 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         // bits consumed since `start`; a restart interval must end exactly at its marker
         // (decoder.cpp:296-302 aligns to the byte boundary and expects RSTn there)
-        const uint64_t bits = (uint64_t)br.words_consumed() * 32u + br.bitpos - bit0;
+        const uint32_t nw = WIDE ? br.words_consumed() : reinterpret_cast<BitReader<1> &>(br).words_fetched();
+        const uint64_t bits = (uint64_t)nw * 32u + br.bitpos - bit0;
         const uint64_t used = (bits + 7u) >> 3;
         const uint64_t avail = (uint64_t)end - start;
         if (used > avail) err |= B2J_ST_OVERRUN;
@@ -1055,7 +1060,7 @@ __device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict
     if (p < limit)
     {
         BitReader<1> br;
-        br.init(base + (p >> 3));
+        br.init(base, p >> 3);
         const uint32_t bit0 = br.bitpos;
         br.bitpos += p & 7u;
         const uint32_t p_byte = p & ~7u;
