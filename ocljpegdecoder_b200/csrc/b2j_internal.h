@@ -25,13 +25,16 @@ constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
 constexpr uint32_t kNoTerm = 0xFFFFu;
 
-// LUT entry (u16), laid out so that the decode loop needs no arithmetic on the fields:
-//   leaf    : bits 0-5  = 32 + code length (33..48)      -> bit position advances by field0 - field1
-//             bits 6-11 = 32 - value-bit count (16..32)     (AC: size nibble; DC: category)
-//             bits 12-15 = zero run
-//   escape  : bits 0-5  = extra index bits nb (1..16-kLutBits, i.e. < 32), bits 6-15 = sub-table
+// LUT entry (u16):
+//   leaf    : bits 0-4  = code length (1..16), bit 5 = 1
+//             AC tables: bits 6-9 = value-bit count (size nibble), bits 10-15 = zero run (0..15); the
+//                        end-of-block symbol 0x00 carries run kRunEob = 63, so that it ends the block through
+//                        the ordinary "position >= 64" test of the decode loop
+//             DC tables: bits 6-10 = value-bit count (category 0..16)
+//   escape  : bits 0-5  = extra index bits nb (1..16-kLutBits, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
 //             offset relative to the end of the primary table
 //   invalid : 0 (no codeword has this prefix)
+constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubMax = 1024;    // sub-table entries addressable by an escape
 
 // sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)

@@ -15,10 +15,13 @@ namespace b2j {
 namespace {
 inline uint16_t leaf_entry(int len, int sym, bool is_dc)
 {
-    int size, run;
-    if (is_dc) { size = sym; run = 0; if (size > 16) return 0; }   // category > 16: not decodable here
-    else { size = sym & 15; run = sym >> 4; }
-    return (uint16_t)((32 + len) | ((32 - size) << 6) | (run << 12));
+    if (is_dc)
+    {
+        if (sym > 16) return 0;   // category > 16: not decodable here
+        return (uint16_t)(len | 32 | (sym << 6));
+    }
+    const int size = sym & 15, run = sym == 0 ? (int)kRunEob : (sym >> 4);
+    return (uint16_t)(len | 32 | (size << 6) | (run << 10));
 }
 } // namespace
 

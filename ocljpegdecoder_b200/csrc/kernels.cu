@@ -811,13 +811,13 @@ __device__ __forceinline__ uint32_t lut_second(uint32_t tab, uint32_t pk, uint32
     return e;
 }
 
-// Value bits -> signed coefficient (JPEG EXTEND, decoder.cpp:72-82). v: the bits left-aligned,
-// s32 = 32 - bit count (32 -> no bits -> 0). A leading 1 bit means positive.
-__device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
+// Value bits -> signed coefficient (JPEG EXTEND, decoder.cpp:72-82). v: the bits left-aligned, size = their
+// number (0 -> 0). A leading 1 bit means positive.
+__device__ __forceinline__ int32_t extend_sz(uint32_t v, uint32_t size)
 {
-    const uint32_t u = __funnelshift_rc(v, 0u, s32);                 // the value bits as a number (no bits -> 0)
+    const uint32_t u = __funnelshift_l(v, 0u, size);                 // the value bits as a number: v >> (32 - size)
     const uint32_t neg = (uint32_t)((int32_t)~v >> 31);              // all ones when the leading bit is 0
-    return (int32_t)(u - __funnelshift_rc(neg, 0u, s32));            // negative: u - (2^size - 1)
+    return (int32_t)(u - __funnelshift_l(neg, 0u, size));            // negative: u - (2^size - 1)
 }
 
 // SYNC = false: a lane is a restart interval (byte-aligned start from seg_start[], DC predictors 0, the
@@ -825,6 +825,7 @@ __device__ __forceinline__ int32_t extend_s32(uint32_t v, uint32_t s32)
 // SYNC = true : a lane is a sub-sequence of a stream without restart markers; its first block, bit
 //   position, MCU phase, block index and DC predictors come from the self-synchronisation passes
 //   (SubRec / SubPre), and the table choice is per lane.
+constexpr uint32_t kZzBytes = 128;
 template <bool RING> struct ReaderOf { typedef BitReader<1> type; };
 template <> struct ReaderOf<true> { typedef RingReader type; };
 
@@ -838,9 +839,10 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     extern __shared__ __align__(16) uint8_t smem[];
     // [ per-lane block slots: kHuffThreads * 128 B ][ zig-zag byte offsets: 64 B ][ LUT set ]
     uint8_t *s_slots = smem;
-    uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory
+    uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory;
+                                                                // 128 entries: a corrupt block may run up to 15 positions past 63
     constexpr uint32_t kRingBytes = WIDE ? kHuffThreads * 32 : 0;   // [ ... ][ per-lane stream rings ][ LUT set ]
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + 64 + kRingBytes);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + kZzBytes + kRingBytes);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -853,7 +855,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         for (uint32_t k = tid; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
         uint4 *z = reinterpret_cast<uint4 *>(s_slots);
         for (uint32_t k = tid; k < kHuffThreads * 8; k += kHuffThreads) z[k] = make_uint4(0, 0, 0, 0);
-        if (tid < 64) s_zz2[tid] = c_zigzag2[tid];
+        if (tid < kZzBytes) s_zz2[tid] = tid < 64 ? c_zigzag2[tid] : (uint8_t)0;
     }
     __syncthreads();
 
@@ -905,7 +907,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 
     typename ReaderOf<WIDE>::type br;
     const uint8_t *base = clean + im.raw_off;
-    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + 64 + tid * 32u);
+    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + kZzBytes + tid * 32u);
     else reinterpret_cast<BitReader<1> &>(br).init(base, decodable ? start : 0u);
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
     if (SYNC) br.bitpos += start_bit & 7u;
@@ -914,7 +916,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint32_t sm_base;   // kept opaque: otherwise the shared-window base is re-derived (S2R) inside the decode loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_addr(smem)));
     const uint32_t sm_zz = sm_base + kHuffThreads * 128;
-    const uint32_t sm_lut = sm_zz + 64 + kRingBytes;
+    const uint32_t sm_lut = sm_zz + kZzBytes + kRingBytes;
     // shared address of this lane's slot with the chunk swizzle folded in: coefficient n lives at
     // slot + ((n>>3) ^ (lane&7))*16 + (n&7)*2 == slot_key ^ (2n)   (slots are 128-byte aligned)
     const uint32_t slot_key = sm_base + tid * 128u + ((lane & 7u) << 4);
@@ -936,9 +938,9 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
             if (!(e & 32u)) { err |= B2J_ST_BAD_CODE; dead = true; }
             else
             {
-                uint32_t lenx = e & 63u, s32 = (e >> 6) & 63u;
-                const int32_t diff = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
-                br.bitpos += lenx - s32;      // (32 + len) - (32 - size)
+                uint32_t len = e & 31u, size = (e >> 6) & 31u;
+                const int32_t diff = extend_sz(pk << len, size);
+                br.bitpos += len + size;
                 br.refill();
                 int32_t dcv;
                 if (comp == 0) { dc0 += diff; dcv = dc0; }
@@ -946,45 +948,30 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
                 else { dc2 += diff; dcv = dc2; }
                 if (dcv != (int32_t)(int16_t)dcv) err |= B2J_ST_DC_RANGE;
                 sts_u16(slot_key, (uint32_t)dcv);
-                // ---- AC (decoder.cpp:236-258). The store of coefficient i is issued one iteration late, behind
-                // the table lookup of symbol i+1: its zig-zag lookup then never stalls the in-order warp.
-                uint32_t pos = 1, pend_zz = 0, pend_v = 0;
-                bool pend = false;
+                // ---- AC (decoder.cpp:236-258). The end-of-block code carries a run of 63 in the table, so it
+                // leaves the loop through the ordinary position test and costs no test of its own.
+                uint32_t pos = 1;
                 while (true)
                 {
                     pk = br.peek();
                     e = lut_first(ac_tab, pk);
-                    if (DEFER)
-                    {
-                        if (pend) sts_u16(slot_key ^ pend_zz, pend_v);
-                        pend = false;
-                    }
                     if (!(e & 32u))
                     {
                         e = lut_second(ac_tab, pk, e);
                         if (!(e & 32u)) { err |= B2J_ST_BAD_CODE; dead = true; break; }
                     }
-                    lenx = e & 63u;
-                    const uint32_t rs = e >> 6;            // run << 6 | (32 - size)
-                    s32 = rs & 63u;
-                    const int32_t v = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
-                    br.bitpos += lenx - s32;
+                    len = e & 31u;
+                    size = (e >> 6) & 15u;
+                    const int32_t v = extend_sz(pk << len, size);
+                    br.bitpos += len + size;
                     br.refill();
-                    if (rs == 32u) break;                   // run == 0 && size == 0: EOB
-                    pos += e >> 12;
-                    if (s32 != 32u && pos < 64u)
-                    {
-                        if (DEFER) { pend_zz = lds_u8(sm_zz + pos); pend_v = (uint32_t)v; pend = true; }
-                        else sts_u16(slot_key ^ lds_u8(sm_zz + pos), (uint32_t)v);
-                    }
+                    pos += e >> 10;          // zero run
+                    if (size) sts_u16(slot_key ^ lds_u8(sm_zz + pos), (uint32_t)v);   // pos < 128: the table is padded
                     pos++;   // past the stored coefficient, or the extra zero of a size-0 run (decoder.cpp:247-252)
-                    if (pos >= 64u)
-                    {
-                        if (pos > 64u) { err |= B2J_ST_BLOCK_OVERFLOW; dead = true; }   // decoder.cpp:259
-                        break;
-                    }
+                    if (pos >= 64u) break;
                 }
-                if (DEFER && pend) sts_u16(slot_key ^ pend_zz, pend_v);
+                // more than 64 coefficients without an end-of-block code (decoder.cpp:259)
+                if (!dead && pos > 64u && (e >> 10) != kRunEob) { err |= B2J_ST_BLOCK_OVERFLOW; dead = true; }
             }
         }
         __syncwarp();
@@ -1075,20 +1062,25 @@ __device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict
                 e = lut_second(tab, pk, e);
                 if (!(e & 32u)) { bad = true; break; }
             }
-            const uint32_t lenx = e & 63u, rs = e >> 6, s32 = rs & 63u;
+            const uint32_t len = e & 31u;
+            uint32_t size;
             if (z == 0u)
             {
+                size = (e >> 6) & 31u;
                 // DC code: a block starts here
                 if (r.fs == kSubNone) { r.fs = p; r.fc = c; }
                 r.nblk++;
-                const int32_t diff = extend_s32(__funnelshift_l(0u, pk, lenx), s32);
+                const int32_t diff = extend_sz(pk << len, size);
                 if (comp == 0u) r.dc0 += diff; else if (comp == 1u) r.dc1 += diff; else r.dc2 += diff;
                 z = 1u;
                 tab = sm_lut + 2u * (uint32_t)s_lut[3u + comp];
             }
-            else if (rs == 32u) z = 64u;      // EOB
-            else z += (e >> 12) + 1u;         // zero run + the coefficient (or the extra zero of a size-0 run)
-            br.bitpos += lenx - s32;
+            else
+            {
+                size = (e >> 6) & 15u;
+                z += (e >> 10) + 1u;          // zero run + the coefficient (or the extra zero of a size-0 run); EOB: run 63
+            }
+            br.bitpos += len + size;
             br.refill();
             p = p_byte + br.nref * 32u + br.bitpos - bit0;
             if (z >= 64u)
@@ -1718,7 +1710,7 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
 
 // =====================================================================================
 // Launchers (host).
-size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + 64 + (ring ? (size_t)kHuffThreads * 32 : 0) + (size_t)max_lut_len * 2; }
+size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + kZzBytes + (ring ? (size_t)kHuffThreads * 32 : 0) + (size_t)max_lut_len * 2; }
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {

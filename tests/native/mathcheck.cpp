@@ -54,7 +54,14 @@ int chk_lut_decode(const uint8_t counts[16], const uint8_t *symbols, int is_dc, 
         e = t[(1u << b2j::kLutBits) + off + ((peek << b2j::kLutBits) >> (32u - nb))];
         if (e == 0) return 0;
     }
-    const int len = (int)(e & 63u) - 32, size = 32 - (int)((e >> 6) & 63u), run = (int)(e >> 12);
+    const int len = (int)(e & 31u);
+    int size, run;
+    if (is_dc) { size = (int)((e >> 6) & 31u); run = 0; }
+    else
+    {
+        size = (int)((e >> 6) & 15u); run = (int)(e >> 10);
+        if (run == (int)b2j::kRunEob) run = 0;   // the end-of-block symbol 0x00
+    }
     return len | (size << 8) | (run << 16);
 }
 
