@@ -334,7 +334,7 @@ def main():
                          "frac": round(achieved / peak, 4), "traffic": measured_traffic(kb[dom][0]), "peak_source": peak_src,
                          "bytes_per_launch": kb[dom][1], "launch_ms": round(stage[dom], 4),
                          "pipeline": {"achieved": round(pipe, 1), "frac": round(pipe / peak, 4),
-                                      "note": "all 5 kernels: (C + 2*128*B + 4*W*H) / step time, SURVEY.md 8(d)"},
+                                      "note": "all kernels of a step (pre-pass, Huffman, IDCT+colour): (C + 2*128*B + 4*W*H) / step time, SURVEY.md 8(d)"},
                          "stage_ms": {k: round(v, 4) for k, v in stage.items()},
                          "huffman_gbit_s": round(info.scan_bytes * 8 / (stage["huffman_ms"] * 1e-3) / 1e9, 1)},
             "cpu_baseline": cpu,

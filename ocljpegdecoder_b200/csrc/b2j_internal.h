@@ -17,7 +17,11 @@ constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of r
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
 constexpr int kSubBytes = 128;           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
 constexpr int kSyncRounds = 6;           // parallel synchronisation rounds before the sequential sweep
-constexpr int kLutBits = 10;             // primary Huffman LUT width
+#ifndef B2J_LUT_BITS
+#define B2J_LUT_BITS 10
+#endif
+constexpr int kLutBits = B2J_LUT_BITS;   // primary Huffman LUT width, AC tables (one lookup per coefficient)
+constexpr int kLutBitsDc = 6;            // DC tables (one lookup per block): small, the shared memory goes to the stream rings
 constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set
 constexpr int kLutMaxEntries = 12288;    // u16 entries of one LUT set (24 KB of shared memory)
 constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
@@ -31,11 +35,11 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //                        end-of-block symbol 0x00 carries run kRunEob = 63, so that it ends the block through
 //                        the ordinary "position >= 64" test of the decode loop
 //             DC tables: bits 6-10 = value-bit count (category 0..16)
-//   escape  : bits 0-5  = extra index bits nb (1..16-kLutBits, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
-//             offset relative to the end of the primary table
+//   escape  : bits 0-5  = extra index bits nb (1..16 - primary width, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
+//             offset relative to the end of the primary table, in units of kLutSubAlign entries
 //   invalid : 0 (no codeword has this prefix)
 constexpr uint32_t kRunEob = 63;
-constexpr uint32_t kLutSubMax = 1024;    // sub-table entries addressable by an escape
+constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table
 
 // sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)
 enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3 };

@@ -27,7 +27,7 @@ inline uint16_t leaf_entry(int len, int sym, bool is_dc)
 
 bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out, size_t max_entries)
 {
-    constexpr int K = kLutBits;
+    const int K = is_dc ? kLutBitsDc : kLutBits;
     struct Code { uint32_t code; int len; int sym; };
     Code codes[256];
     int n = 0;
@@ -66,10 +66,11 @@ bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
     {
         if (!maxlen[p]) continue;
         const int nb = maxlen[p] - K;
+        while ((out.size() - ((size_t)1 << K)) % kLutSubAlign) out.push_back(0);   // escapes address sub-tables in units of kLutSubAlign
         const size_t rel = out.size() - ((size_t)1 << K);
-        if (rel + ((size_t)1 << nb) > kLutSubMax) return false;
+        if (rel / kLutSubAlign >= 1024) return false;
         sub_off[p] = (uint32_t)out.size();
-        out[p] = (uint16_t)(nb | (rel << 6));
+        out[p] = (uint16_t)(nb | ((rel / kLutSubAlign) << 6));
         out.resize(out.size() + ((size_t)1 << nb), 0);
         if (out.size() > max_entries) return false;
     }

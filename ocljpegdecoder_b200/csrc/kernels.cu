@@ -731,46 +731,94 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
 }
 
-// Bit reader whose stream arrives through a per-lane ring in shared memory filled by cp.async (LDGSTS):
-// 2 x 16 bytes per lane; the chunk behind the one being read is requested when the reader enters a
-// chunk, i.e. four window shifts (>= 128 bits, some twenty symbols) before its first word is needed,
-// and the copy never occupies a register. Every global sector is fetched once (16 bytes per request)
-// instead of once per 4-byte word as with plain loads, which miss L1 here: at 25 warps per SM the
-// streams of 896 lanes do not fit in the ~32 KB of L1 that the shared-memory carve-out leaves.
+// Bit reader whose stream arrives through a per-lane ring in shared memory filled by cp.async (LDGSTS).
+// Why: with plain loads the look-ahead word of BitReader is the destination of a predicated LDG in nearly every
+// iteration of the decode loop (some lane of the warp always refills) and the source of the byte swap of the
+// NEXT iteration's refill. The scoreboard tracks registers per warp, not per lane, so every iteration waits for
+// the L2 round trip of the previous one -- a quarter of all stall samples of the kernel sat on that one PRMT.
+// Here no register is ever the target of a global load. The ring holds kRingChunks x 16 bytes per lane;
+// chunks are requested at the warp-synchronous point between two blocks (top_up) and one cp.async group is
+// committed there per block round, so "all groups but the newest have landed" (wait_group 1, which in steady
+// state never waits: a round is thousands of cycles) proves that everything requested in earlier rounds is
+// present. A lane that runs ahead of what is known to have landed -- a block of more than ~32 bytes -- requests
+// and waits on the spot (rare at photographic qualities; the cost is the stall the plain reader pays always).
+constexpr uint32_t kRingChunks = 4;
+constexpr uint32_t kRingBytesPerLane = kRingChunks * 16;
+
+// Out of line on purpose: the rare "ran ahead of the landed data" path must not bloat the decode loop.
+// Requests every chunk below `limit` that is still missing, waits for all of them, returns the new request mark.
+__device__ __noinline__ uint32_t ring_catch_up(uint32_t ring, const uint8_t *gbase, uint32_t req, uint32_t limit)
+{
+    while (req < limit)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + (req & (kRingBytesPerLane - 1u))), "l"(gbase + req) : "memory");
+        req += 16u;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return req;
+}
+
 struct RingReader
 {
     uint32_t cur, nxt;     // big-endian words: `cur` holds the bit at `bitpos`
+    uint32_t raw;          // look-ahead word (memory byte order) read from the ring one refill early
     uint32_t bitpos;       // 0..31 after refill()
-    uint32_t w4;           // 4 * index of the next stream word to enter the window (from the 16-byte aligned base)
-    uint32_t w4_0;         // its value after init(): consumed words = (w4 - w4_0) / 4
-    uint32_t ring;         // shared address of this lane's 32-byte ring
-    const uint8_t *gbase;  // 16-byte aligned global address of stream word 0
+    uint32_t w4;           // byte index (from gbase) of the next word to read from the ring
+    uint32_t w4_0;         // its value after init(): words entered into the window = (w4 - w4_0) / 4
+    uint32_t req;          // byte index up to which chunks have been requested (multiple of 16)
+    uint32_t landed;       // byte index up to which chunks are known to have landed
+    uint32_t ring;         // shared address of this lane's ring
+    const uint8_t *gbase;  // 16-byte aligned global address of stream byte 0
 
-    __device__ __forceinline__ void fetch(uint32_t chunk)
+    __device__ __forceinline__ void request_upto(uint32_t limit)
     {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + ((chunk & 1u) << 4)), "l"(gbase + (size_t)chunk * 16u) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        while (req < limit)
+        {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + (req & (kRingBytesPerLane - 1u))), "l"(gbase + req) : "memory");
+            req += 16u;
+        }
     }
-    __device__ __forceinline__ uint32_t word(uint32_t byte_index) const
+    // the chunk that holds word w4 and the kRingChunks-1 behind it: never overwrites a chunk still to be read
+    __device__ __forceinline__ void top_up() { request_upto((w4 & ~15u) + kRingBytesPerLane); }
+    // between two blocks, all lanes of the warp together
+    __device__ __forceinline__ void round_boundary()
+    {
+        const uint32_t before = req;
+        top_up();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        landed = before;
+    }
+    __device__ __forceinline__ void catch_up()
+    {
+        req = ring_catch_up(ring, gbase, req, (w4 & ~15u) + kRingBytesPerLane);
+        landed = req;
+    }
+    // once per symbol, in front of the window shift: the next ring word must have landed
+    __device__ __forceinline__ void ensure()
+    {
+        if (__builtin_expect(w4 >= landed, 0)) catch_up();
+    }
+    __device__ __forceinline__ uint32_t ring_word(uint32_t byte_index) const
     {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring | (byte_index & 28u)) : "memory");
-        return __byte_perm(v, 0, 0x0123);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (byte_index & (kRingBytesPerLane - 4u))) : "memory");
+        return v;
     }
     __device__ __forceinline__ void init(const uint8_t *p, uint32_t ring_addr)
     {
         const uint32_t a16 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
         gbase = p - a16;
         ring = ring_addr;
-        fetch(0);
-        fetch(1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint32_t ws = a16 & 12u;       // byte index of the word that holds p
-        cur = word(ws);
-        nxt = word(ws + 4u);
-        w4 = ws + 8u;
-        if (w4 >= 16u) { fetch(2); asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // chunk 0 is already used up
-        w4_0 = w4;
+        req = 0u;
+        w4 = a16 & 12u;      // the word that holds p
+        catch_up();
+        cur = __byte_perm(ring_word(w4), 0, 0x0123);
+        nxt = __byte_perm(ring_word(w4 + 4u), 0, 0x0123);
+        raw = ring_word(w4 + 8u);
+        w4 += 12u;
+        w4_0 = w4 - 4u;      // `raw` has not entered the window yet
         bitpos = (a16 & 3u) * 8u;
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
@@ -779,34 +827,29 @@ struct RingReader
         if (bitpos >= 32u)
         {
             cur = nxt;
-            nxt = word(w4);
+            nxt = __byte_perm(raw, 0, 0x0123);
+            raw = ring_word(w4);
             w4 += 4u;
             bitpos -= 32u;
-            if ((w4 & 12u) == 0u)
-            {
-                // entering chunk w4/16: the chunk behind it goes into the slot just drained; all older copies have landed
-                fetch((w4 >> 4) + 1u);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            }
         }
     }
-    __device__ __forceinline__ uint32_t words_consumed() const { return (w4 - w4_0) >> 2; }
+    __device__ __forceinline__ uint32_t words_consumed() const { return (w4 - 4u - w4_0) >> 2; }
 };
 
 // One symbol from a two-level LUT in shared memory (entry format: b2j_internal.h). `tab` is the
 // shared-window byte address of the table. Returns the leaf entry, 0 when no codeword matches.
-__device__ __forceinline__ uint32_t lut_first(uint32_t tab, uint32_t pk)
+__device__ __forceinline__ uint32_t lut_first(uint32_t tab, uint32_t pk, uint32_t bits = kLutBits)
 {
-    return lds_u16(tab + ((pk >> (32 - kLutBits)) << 1));
+    return lds_u16(tab + ((pk >> (32u - bits)) << 1));
 }
 // Second level, taken when bit 5 of the first-level entry is clear (bit 5 is set in every leaf:
 // 32 + len). Returns a leaf, or 0 when the bits are no codeword.
-__device__ __forceinline__ uint32_t lut_second(uint32_t tab, uint32_t pk, uint32_t e)
+__device__ __forceinline__ uint32_t lut_second(uint32_t tab, uint32_t pk, uint32_t e, uint32_t bits = kLutBits)
 {
     if (e != 0u)
     {
-        const uint32_t nb = e & 63u, off = e >> 6;
-        e = lds_u16(tab + (((1u << kLutBits) + off + ((pk << kLutBits) >> (32u - nb))) << 1));
+        const uint32_t nb = e & 63u, off = (e >> 6) * kLutSubAlign;
+        e = lds_u16(tab + (((1u << bits) + off + ((pk << bits) >> (32u - nb))) << 1));
     }
     return e;
 }
@@ -841,7 +884,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint8_t *s_slots = smem;
     uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory;
                                                                 // 128 entries: a corrupt block may run up to 15 positions past 63
-    constexpr uint32_t kRingBytes = WIDE ? kHuffThreads * 32 : 0;   // [ ... ][ per-lane stream rings ][ LUT set ]
+    constexpr uint32_t kRingBytes = WIDE ? kHuffThreads * kRingBytesPerLane : 0;   // [ ... ][ per-lane stream rings ][ LUT set ]
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + kZzBytes + kRingBytes);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -907,7 +950,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 
     typename ReaderOf<WIDE>::type br;
     const uint8_t *base = clean + im.raw_off;
-    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + kZzBytes + tid * 32u);
+    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + kZzBytes + tid * kRingBytesPerLane);
     else reinterpret_cast<BitReader<1> &>(br).init(base, decodable ? start : 0u);
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
     if (SYNC) br.bitpos += start_bit & 7u;
@@ -932,9 +975,10 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         if (mine && !dead)
         {
             // ---- DC (decoder.cpp:226-233)
+            if (WIDE) reinterpret_cast<RingReader &>(br).ensure();
             uint32_t pk = br.peek();
-            uint32_t e = lut_first(dc_tab, pk);
-            if (!(e & 32u)) e = lut_second(dc_tab, pk, e);
+            uint32_t e = lut_first(dc_tab, pk, kLutBitsDc);
+            if (!(e & 32u)) e = lut_second(dc_tab, pk, e, kLutBitsDc);
             if (!(e & 32u)) { err |= B2J_ST_BAD_CODE; dead = true; }
             else
             {
@@ -953,6 +997,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
                 uint32_t pos = 1;
                 while (true)
                 {
+                    if (WIDE) reinterpret_cast<RingReader &>(br).ensure();
                     pk = br.peek();
                     e = lut_first(ac_tab, pk);
                     if (!(e & 32u))
@@ -993,6 +1038,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
             }
         }
         __syncwarp();
+        if (WIDE) reinterpret_cast<RingReader &>(br).round_boundary();
         bi = (bi + 1 == tot) ? 0u : bi + 1;
     }
 
@@ -1056,10 +1102,11 @@ __device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict
         while (p < limit)
         {
             const uint32_t pk = br.peek();
-            uint32_t e = lut_first(tab, pk);
+            const uint32_t bits = z == 0u ? (uint32_t)kLutBitsDc : (uint32_t)kLutBits;
+            uint32_t e = lut_first(tab, pk, bits);
             if (!(e & 32u))
             {
-                e = lut_second(tab, pk, e);
+                e = lut_second(tab, pk, e, bits);
                 if (!(e & 32u)) { bad = true; break; }
             }
             const uint32_t len = e & 31u;
@@ -1710,7 +1757,7 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
 
 // =====================================================================================
 // Launchers (host).
-size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + kZzBytes + (ring ? (size_t)kHuffThreads * 32 : 0) + (size_t)max_lut_len * 2; }
+size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + kZzBytes + (ring ? (size_t)kHuffThreads * kRingBytesPerLane : 0) + (size_t)max_lut_len * 2; }
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {

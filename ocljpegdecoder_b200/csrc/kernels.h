@@ -41,7 +41,7 @@ struct DecodeArgs
     bool use_tma;
     bool any_wide_q;         // some quantiser of the batch exceeds 255 (16-bit DQT): generic dequantisation
     bool prepass_fused;      // single-pass pre-pass (default); B2J_PREPASS=3 selects the three-kernel one
-    uint32_t huff_variant;   // bit 0: 128-bit stream prefetch, bit 1: deferred coefficient store
+    uint32_t huff_variant;   // bit 0: stream through the per-lane cp.async rings (default); B2J_HUFF_VARIANT=0: plain loads
 };
 
 // A contiguous group of images of a batch: the unit the two-stream pipeline works on.

@@ -46,12 +46,13 @@ int chk_lut_decode(const uint8_t counts[16], const uint8_t *symbols, int is_dc, 
     std::vector<uint16_t> t;
     if (!b2j::build_huff_lut(counts, symbols, is_dc != 0, t, b2j::kLutMaxEntries)) return -1;
     if (n_entries) *n_entries = (int)t.size();
-    uint32_t e = t[peek >> (32 - b2j::kLutBits)];
+    const uint32_t K = is_dc ? b2j::kLutBitsDc : b2j::kLutBits;
+    uint32_t e = t[peek >> (32 - K)];
     if ((e & 63u) < 32u)
     {
         if (e == 0) return 0;
-        const uint32_t nb = e & 63u, off = e >> 6;
-        e = t[(1u << b2j::kLutBits) + off + ((peek << b2j::kLutBits) >> (32u - nb))];
+        const uint32_t nb = e & 63u, off = (e >> 6) * b2j::kLutSubAlign;
+        e = t[(1u << K) + off + ((peek << K) >> (32u - nb))];
         if (e == 0) return 0;
     }
     const int len = (int)(e & 31u);

@@ -350,29 +350,33 @@ def test_robust_mode_decodes_files_with_comments(decoder, oracle):
     _check_pixels(outs[1], bgra)
 
 
-def test_prepass_variants_agree(decoder):
-    """The single-pass pre-pass (default) and the three-kernel one (B2J_PREPASS=3) must produce identical
-    planes, pixels and status words: many chunks per image (several look-back windows), streams that end in
-    the middle of a chunk (dead chunks behind), no restart markers, broken restart numbering."""
+def test_kernel_variants_agree(decoder):
+    """The kernel variants kept for measurement -- three-kernel pre-pass (B2J_PREPASS=3) and the Huffman decoder
+    fed through per-lane cp.async rings (B2J_HUFF_VARIANT=1) -- must produce the same planes, pixels and status
+    words as the defaults: many chunks per image (several look-back windows), streams that end in the middle of
+    a chunk (dead chunks behind), no restart markers, broken restart numbering, dense q100 blocks (ring underflow)."""
     good = synth.synth_jpeg(320, 240, 5, 90, "420", 4)
     b = bytearray(good)
     k = good.index(b"\xff\xd1")
     b[k + 1] = 0xD5
     big = synth.synth_jpeg(2560, 1600, 91, 97, "444", 7)          # > 64 chunks of 16 KiB
     files = [big, synth.synth_jpeg(1600, 1200, 92, 95, "444", 0), good, bytes(b), big[:len(big) // 2],
-             synth.synth_jpeg(640, 480, 93, 75, "420", 0), _crafted((2, 2), 80, 48, 2, 3, seed=3, stuffed=True)]
+             synth.synth_jpeg(640, 480, 93, 75, "420", 0), _crafted((2, 2), 80, 48, 2, 3, seed=3, stuffed=True),
+             synth.synth_jpeg(800, 608, 94, 100, "420", 3, optimize=True)]
     assert (len(big) + 16383) // 16384 > 64
     res = {}
-    for variant in ("3", "1"):
-        os.environ["B2J_PREPASS"] = variant
+    for name, env in (("default", {}), ("prepass3", {"B2J_PREPASS": "3"}), ("ring", {"B2J_HUFF_VARIANT": "1"})):
+        os.environ.update(env)
         try:
-            res[variant] = _decode(decoder, files)
+            res[name] = _decode(decoder, files)
         finally:
-            del os.environ["B2J_PREPASS"]
-    st3, c3, p3 = res["3"]
-    st1, c1, p1 = res["1"]
-    assert st3.tolist() == st1.tolist()
-    assert st1[0] == 0 and st1[1] == 0 and st1[3] != 0 and st1[4] != 0
-    for i in range(len(files)):
-        assert np.array_equal(c3[i], c1[i]), i
-        assert np.array_equal(p3[i], p1[i]), i
+            for key in env:
+                del os.environ[key]
+    st0, c0, p0 = res["default"]
+    assert st0[0] == 0 and st0[1] == 0 and st0[3] != 0 and st0[4] != 0 and st0[7] == 0
+    for name in ("prepass3", "ring"):
+        st, c, p = res[name]
+        assert st.tolist() == st0.tolist(), name
+        for i in range(len(files)):
+            assert np.array_equal(c[i], c0[i]), (name, i)
+            assert np.array_equal(p[i], p0[i]), (name, i)
