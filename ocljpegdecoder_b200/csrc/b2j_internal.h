@@ -70,6 +70,7 @@ struct ImgDev
     uint32_t wide_q;       // 1 when some quantiser value exceeds 255
     uint32_t sub_first;    // self-synchronising path (streams without DRI): first sub-sequence record of this image
     uint32_t n_sub_max;    // upper bound of its sub-sequence count (from raw_len); 0 = restart-interval path
+    uint32_t scta_first;   // its first decode CTA on the self-synchronising path
 };
 
 // Self-synchronising decode, one record per sub-sequence j of kSubBytes*8 bits of clean stream:
@@ -84,7 +85,7 @@ struct SubRec
     uint32_t fs;        // bit position of the first of those blocks (kSubNone: none)
     uint32_t fc;        // its block-in-MCU index
 };
-struct SubPre { uint32_t blk; int32_t dc[3]; };   // exclusive prefix over the sub-sequences of one image
+struct SubPre { uint32_t blk; int32_t dc[3]; };   // exclusive prefix over the sub-sequences of one image (formed inside the decode CTA)
 constexpr uint32_t kSubInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kSubNone = 0xFFFFFFFFu;
 

@@ -868,7 +868,7 @@ __device__ __forceinline__ int32_t extend_sz(uint32_t v, uint32_t size)
 // SYNC = true : a lane is a sub-sequence of a stream without restart markers; its first block, bit
 //   position, MCU phase, block index and DC predictors come from the self-synchronisation passes
 //   (SubRec / SubPre), and the table choice is per lane.
-constexpr uint32_t kZzBytes = 128;
+constexpr uint32_t kZzBytes = 192;   // 128 zig-zag offsets + 64 bytes of scratch for the CTA-wide prefix of the SYNC lanes
 template <bool RING> struct ReaderOf { typedef BitReader<1> type; };
 template <> struct ReaderOf<true> { typedef RingReader type; };
 
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(kHuffThreads)
 k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
               const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ clean_len,
               const uint16_t *__restrict__ luts, int16_t *__restrict__ coef, int32_t *__restrict__ status,
-              const SubRec *__restrict__ recs, const SubPre *__restrict__ pres)
+              const SubRec *__restrict__ recs, const uint4 *__restrict__ cta_base)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     // [ per-lane block slots: kHuffThreads * 128 B ][ zig-zag byte offsets: 64 B ][ LUT set ]
@@ -898,7 +898,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         for (uint32_t k = tid; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
         uint4 *z = reinterpret_cast<uint4 *>(s_slots);
         for (uint32_t k = tid; k < kHuffThreads * 8; k += kHuffThreads) z[k] = make_uint4(0, 0, 0, 0);
-        if (tid < kZzBytes) s_zz2[tid] = tid < 64 ? c_zigzag2[tid] : (uint8_t)0;
+        if (tid < 128) s_zz2[tid] = tid < 64 ? c_zigzag2[tid] : (uint8_t)0;
     }
     __syncthreads();
 
@@ -929,10 +929,33 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         const uint32_t bits = clean_len[cta.img] * 8u;
         const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
         active = seg < n_sub;
+        SubRec rec;
+        rec.nblk = 0; rec.dc[0] = rec.dc[1] = rec.dc[2] = 0;
+        if (active) rec = recs[im.sub_first + seg];
+        // exclusive prefix of (blocks started, DC sums) over the sub-sequences in front of this lane: the CTA's base
+        // (k_sync_cta_scan) plus the lanes in front of it inside the CTA
+        SubPre pre;
+        {
+            uint4 *s_wtot = reinterpret_cast<uint4 *>(smem + kHuffThreads * 128 + 128);   // static shared memory would misalign the slots
+            uint32_t ib = rec.nblk; int32_t i0 = rec.dc[0], i1 = rec.dc[1], i2 = rec.dc[2];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t tb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+                const int32_t t0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), t1 = __shfl_up_sync(0xFFFFFFFFu, i1, o), t2 = __shfl_up_sync(0xFFFFFFFFu, i2, o);
+                if (lane >= (uint32_t)o) { ib += tb; i0 += t0; i1 += t1; i2 += t2; }
+            }
+            if (lane == 31u) s_wtot[tid >> 5] = make_uint4(ib, (uint32_t)i0, (uint32_t)i1, (uint32_t)i2);
+            __syncthreads();
+            uint4 acc = cta_base[blockIdx.x];
+#pragma unroll
+            for (int w = 0; w < kHuffThreads / 32; w++)
+                if (w < (int)(tid >> 5)) { const uint4 t = s_wtot[w]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+            pre.blk = acc.x + ib - rec.nblk;
+            pre.dc[0] = (int32_t)acc.y + i0 - rec.dc[0]; pre.dc[1] = (int32_t)acc.z + i1 - rec.dc[1]; pre.dc[2] = (int32_t)acc.w + i2 - rec.dc[2];
+        }
         if (active)
         {
-            const SubRec rec = recs[im.sub_first + seg];
-            const SubPre pre = pres[im.sub_first + seg];
             if (rec.fs != kSubNone && pre.blk < im.blk_count)
             {
                 nblk = min(rec.nblk, im.blk_count - pre.blk);           // bits behind the last block decode to junk blocks: dropped
@@ -1156,13 +1179,22 @@ __device__ __forceinline__ void store_rec(SubRec *__restrict__ dst, const WalkRe
     reinterpret_cast<uint4 *>(dst)[1] = b;
 }
 
-// round 0: lane j walks sub-sequence j from the guessed state. round >= 1: lane j walks sub-sequence j+1
-// from the exit state recorded for j (all lanes in round 1, afterwards only where that state changed
-// in the previous round).
+// Appends sub-sequence k of image img to the work list of the next round (its exit state has just changed).
+__device__ __forceinline__ void sync_flag_changed(uint32_t img, uint32_t k, uint32_t round, uint32_t last_round, uint32_t *__restrict__ cnt,
+                                                  uint2 *__restrict__ out_list, uint32_t *__restrict__ stamp)
+{
+    const uint32_t slot = atomicAdd(&cnt[round], 1u);   // also the convergence evidence: exit states this round still changed
+    out_list[slot] = make_uint2(img, k);
+    if (round == last_round) stamp[k] = round;          // what the sequential sweep repairs
+}
+
+// Rounds 0 and 1, one lane per sub-sequence. round 0: lane j walks sub-sequence j from the guessed state.
+// round 1: lane j walks sub-sequence j+1 from the exit state recorded for j; where that replaces a different
+// exit state, sub-sequence j+1 goes on the work list of round 2.
 __global__ void __launch_bounds__(kHuffThreads)
 k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
-            uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ stats)
+            uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ cnt, uint2 *__restrict__ out_list)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
@@ -1172,14 +1204,6 @@ k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, 
     const uint32_t bits = clean_len[cta.img] * 8u;
     const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
     if (cta.seg_first >= n_sub) return;   // uniform: the clean stream is shorter than the raw bound
-    if (round > 1u && stats[round - 1u] == 0u) return;   // already converged (uniform for the whole grid)
-    if (round > 1u)
-    {
-        // later rounds touch few lanes: leave before staging the tables when none of this CTA's lanes is due
-        const uint32_t jj = cta.seg_first + tid;
-        const bool due = jj + 1u < n_sub && stamps[im.sub_first + jj] == round - 1u;
-        if (!__syncthreads_or(due)) return;
-    }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -1202,28 +1226,97 @@ k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, 
         return;
     }
     if (j + 1u >= n_sub) return;
-    if (round > 1u && stamp[j] != round - 1u) return;
     const uint2 in = *reinterpret_cast<const uint2 *>(rec + j);
     const uint2 old = *reinterpret_cast<const uint2 *>(rec + j + 1);
     const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
     const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((j + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
     store_rec(rec + j + 1, r);
-    if (r.p != old.x || r.cz != old.y)
-    {
-        stamp[j + 1] = round;
-        atomicAdd(&stats[round], 1u);   // how many exit states this round still changed (convergence evidence)
-    }
+    if (r.p != old.x || r.cz != old.y) sync_flag_changed(cta.img, j + 1u, round, (uint32_t)kSyncRounds, cnt, out_list, stamp);
 }
 
-// One warp per image: in-order repair of whatever the last parallel round still changed.
-__global__ void __launch_bounds__(32)
-k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
-             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
-             uint32_t *__restrict__ stamps, uint32_t last_round, uint32_t *__restrict__ stats)
+// Rounds >= 2 touch few sub-sequences, scattered over the whole batch: they run over the compact work list
+// the previous round wrote, one lane per entry, instead of over all sub-sequences (where a warp with one
+// lane due costs as much as a full one). Entry (img, k): the exit state of sub-sequence k changed, so k+1 is
+// walked again from it. Lanes of a CTA may belong to images with different decode tables: the CTA serves one
+// table set at a time (usually there is only one).
+__global__ void __launch_bounds__(kHuffThreads)
+k_sync_walk_list(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ clean_len,
+                 const uint16_t *__restrict__ luts, SubRec *__restrict__ recs, uint32_t *__restrict__ stamps, uint32_t round,
+                 uint32_t *__restrict__ cnt, const uint2 *__restrict__ in_list, uint2 *__restrict__ out_list)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
-    const uint32_t lane = threadIdx.x;
+    __shared__ uint32_t s_pick, s_len;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t count = cnt[round - 1u];
+    uint32_t sm_lut;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
+    uint32_t staged = 0xFFFFFFFFu;
+    for (uint32_t first = blockIdx.x * kHuffThreads; first < count; first += gridDim.x * kHuffThreads)   // uniform for the CTA
+    {
+        const uint32_t t = first + tid;
+        uint2 ent = make_uint2(0u, 0u);
+        uint32_t my_lut = 0xFFFFFFFFu, n_sub = 0u, bits = 0u;
+        if (t < count)
+        {
+            ent = in_list[t];
+            bits = clean_len[ent.x] * 8u;
+            n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+            if (ent.y + 1u < n_sub) my_lut = imgs[ent.x].lut_off;
+        }
+        while (true)
+        {
+            if (tid == 0) s_pick = 0xFFFFFFFFu;
+            __syncthreads();
+            if (my_lut != 0xFFFFFFFFu) atomicMin(&s_pick, my_lut);
+            __syncthreads();
+            const uint32_t pick = s_pick;
+            if (pick == 0xFFFFFFFFu) break;   // every entry of this batch is done (uniform)
+            if (pick != staged)
+            {
+                if (my_lut == pick) s_len = imgs[ent.x].lut_len;
+                __syncthreads();
+                const uint4 *src = reinterpret_cast<const uint4 *>(luts + pick);
+                uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+                for (uint32_t q = tid; q < s_len / 8; q += kHuffThreads) dst[q] = __ldg(src + q);
+                staged = pick;
+                __syncthreads();
+            }
+            if (my_lut == pick)
+            {
+                const ImgDev &im = imgs[ent.x];
+                const uint32_t k = ent.y;
+                SubRec *rec = recs + im.sub_first;
+                const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
+                const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
+                const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
+                const WalkResult r = walk_subsequence(clean + im.raw_off, sm_lut, s_lut, s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits),
+                                                      im.tot_blks, im.ny_blks);
+                store_rec(rec + k + 1, r);
+                if (r.p != old.x || r.cz != old.y)
+                    sync_flag_changed(ent.x, k + 1u, round, (uint32_t)kSyncRounds, cnt, out_list, stamps + im.sub_first);
+                my_lut = 0xFFFFFFFFu;
+            }
+            __syncthreads();   // the tables may be replaced in the next turn
+        }
+    }
+}
+
+// One CTA per image: in-order repair of whatever the last parallel round still changed (stamp == last_round).
+// All threads look for stamps, one thread chases each change downstream until the stored state is reproduced.
+// Also folds the per-round counters into the batch's convergence statistics.
+constexpr int kSweepThreads = 256;
+__global__ void __launch_bounds__(kSweepThreads)
+k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
+             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
+             uint32_t *__restrict__ stamps, uint32_t last_round, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ stats)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
+    __shared__ uint8_t s_flag[kSweepThreads];
+    const uint32_t tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid >= 1u && tid <= last_round && cnt[tid]) atomicAdd(&stats[tid], cnt[tid]);
+    if (cnt[last_round] == 0u) return;   // converged before the last round: nothing to repair (uniform for the grid)
     const uint32_t img = sync_imgs[blockIdx.x];
     const ImgDev &im = imgs[img];
     const uint32_t bits = clean_len[img] * 8u;
@@ -1232,26 +1325,29 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
     uint32_t *stamp = stamps + im.sub_first;
     const uint8_t *base = clean + im.raw_off;
     bool lut_ready = false;
-    uint32_t sm_lut = 0;
-    for (uint32_t b0 = 0; b0 + 1u < n_sub; b0 += 32u)
+    uint32_t sm_lut = 0, rewalked = 0;
+    for (uint32_t b0 = 0; b0 + 1u < n_sub; b0 += kSweepThreads)
     {
-        const uint32_t j = b0 + lane;
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, j + 1u < n_sub && stamp[j] == last_round);
-        while (mask)
+        const uint32_t j = b0 + tid;
+        const bool flag = j + 1u < n_sub && stamp[j] == last_round;
+        if (!__syncthreads_or(flag)) continue;
+        if (!lut_ready)
         {
-            if (!lut_ready)
+            const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+            for (uint32_t k = tid; k < im.lut_len / 8; k += kSweepThreads) dst[k] = __ldg(src + k);
+            asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
+            lut_ready = true;
+        }
+        s_flag[tid] = flag ? 1 : 0;
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (uint32_t t = 0; t < (uint32_t)kSweepThreads; t++)
             {
-                const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
-                uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-                for (uint32_t k = lane; k < im.lut_len / 8; k += 32u) dst[k] = __ldg(src + k);
-                __syncwarp();
-                asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
-                lut_ready = true;
-            }
-            uint32_t k = b0 + (uint32_t)__ffs(mask) - 1u;
-            mask &= mask - 1u;
-            if (lane == 0)
-            {
+                if (!s_flag[t]) continue;
+                uint32_t k = b0 + t;
+                if (stamp[k] != last_round) continue;   // an earlier chase already passed over it
                 // chase the change downstream until the stored state is reproduced
                 while (k + 1u < n_sub)
                 {
@@ -1261,61 +1357,80 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
                     const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
                     store_rec(rec + k + 1, r);
                     stamp[k] = 0u;
-                    atomicAdd(&stats[7], 1u);   // sub-sequences re-walked by the sequential sweep
+                    rewalked++;
                     if (r.p == old.x && r.cz == old.y) break;
                     k++;
                 }
             }
-            __syncwarp();
         }
+        __syncthreads();   // cleared stamps are visible to the next chunk's readers
+    }
+    if (tid == 0 && rewalked) atomicAdd(&stats[7], rewalked);   // sub-sequences re-walked by the sequential sweep
+}
+
+// Prefix of (blocks started, DC sums) over the sub-sequence records of an image, in two small steps: the totals
+// of every decode CTA (128 consecutive records, read coalesced), then one warp per image turns the CTA totals
+// into exclusive bases. The lanes of k_huff_decode<SYNC> add the part inside their CTA themselves.
+__global__ void __launch_bounds__(kHuffThreads)
+k_sync_cta_totals(const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas, const uint32_t *__restrict__ clean_len,
+                  const SubRec *__restrict__ recs, uint4 *__restrict__ cta_tot)
+{
+    __shared__ uint4 s_w[kHuffThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const HuffCtaDev cta = ctas[blockIdx.x];
+    const ImgDev &im = imgs[cta.img];
+    const uint32_t bits = clean_len[cta.img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    const uint32_t j = cta.seg_first + tid;
+    uint32_t nb = 0; int32_t d0 = 0, d1 = 0, d2 = 0;
+    if (j < n_sub)
+    {
+        const SubRec *rec = recs + im.sub_first + j;
+        const uint4 a = reinterpret_cast<const uint4 *>(rec)[0];
+        const uint2 b = reinterpret_cast<const uint2 *>(rec)[2];
+        nb = a.z; d0 = (int32_t)a.w; d1 = (int32_t)b.x; d2 = (int32_t)b.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o); d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, o);
+        d1 += __shfl_xor_sync(0xFFFFFFFFu, d1, o); d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
+    }
+    if (lane == 0) s_w[tid >> 5] = make_uint4(nb, (uint32_t)d0, (uint32_t)d1, (uint32_t)d2);
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint4 t = s_w[0];
+#pragma unroll
+        for (int w = 1; w < kHuffThreads / 32; w++) { t.x += s_w[w].x; t.y += s_w[w].y; t.z += s_w[w].z; t.w += s_w[w].w; }
+        cta_tot[blockIdx.x] = t;
     }
 }
 
-// One CTA per image: exclusive prefix of (blocks started, DC sums) over its sub-sequence records.
-__global__ void __launch_bounds__(256)
-k_sync_scan(const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs, const uint32_t *__restrict__ clean_len,
-            const SubRec *__restrict__ recs, SubPre *__restrict__ pres)
+// One warp per image: exclusive scan of its CTA totals (in place: totals in, bases out).
+__global__ void __launch_bounds__(32)
+k_sync_cta_scan(const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs, uint4 *__restrict__ cta_tot, uint32_t scta0)
 {
-    __shared__ uint32_t s_blk[256];
-    __shared__ int32_t s_dc[3][256];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t img = sync_imgs[blockIdx.x];
-    const ImgDev &im = imgs[img];
-    const uint32_t bits = clean_len[img] * 8u;
-    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-    const SubRec *rec = recs + im.sub_first;
-    SubPre *pre = pres + im.sub_first;
-    const uint32_t per = (n_sub + 255u) / 256u;
-    const uint32_t j0 = min(tid * per, n_sub), j1 = min(j0 + per, n_sub);
-    uint32_t blk = 0;
-    int32_t d0 = 0, d1 = 0, d2 = 0;
-    for (uint32_t j = j0; j < j1; j++)
+    const uint32_t lane = threadIdx.x;
+    const ImgDev &im = imgs[sync_imgs[blockIdx.x]];
+    const uint32_t n = (im.n_sub_max + kHuffThreads - 1u) / kHuffThreads;
+    uint4 *t = cta_tot + (im.scta_first - scta0);
+    uint4 run = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t b0 = 0; b0 < n; b0 += 32u)
     {
-        const uint4 a = reinterpret_cast<const uint4 *>(rec + j)[0];
-        const uint2 b = reinterpret_cast<const uint2 *>(rec + j)[2];
-        blk += a.z; d0 += (int32_t)a.w; d1 += (int32_t)b.x; d2 += (int32_t)b.y;
-    }
-    s_blk[tid] = blk; s_dc[0][tid] = d0; s_dc[1][tid] = d1; s_dc[2][tid] = d2;
-    __syncthreads();
-    if (tid == 0)   // 256 partial sums: a serial exclusive scan is cheap enough
-    {
-        uint32_t rb = 0; int32_t r0 = 0, r1 = 0, r2 = 0;
-        for (int k = 0; k < 256; k++)
+        const uint32_t k = b0 + lane;
+        const uint4 v = k < n ? t[k] : make_uint4(0u, 0u, 0u, 0u);
+        uint4 x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            const uint32_t tb = s_blk[k]; const int32_t t0 = s_dc[0][k], t1 = s_dc[1][k], t2 = s_dc[2][k];
-            s_blk[k] = rb; s_dc[0][k] = r0; s_dc[1][k] = r1; s_dc[2][k] = r2;
-            rb += tb; r0 += t0; r1 += t1; r2 += t2;
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, x.x, o), b = __shfl_up_sync(0xFFFFFFFFu, x.y, o),
+                           c = __shfl_up_sync(0xFFFFFFFFu, x.z, o), d = __shfl_up_sync(0xFFFFFFFFu, x.w, o);
+            if (lane >= (uint32_t)o) { x.x += a; x.y += b; x.z += c; x.w += d; }
         }
-    }
-    __syncthreads();
-    blk = s_blk[tid]; d0 = s_dc[0][tid]; d1 = s_dc[1][tid]; d2 = s_dc[2][tid];
-    for (uint32_t j = j0; j < j1; j++)
-    {
-        const uint4 a = reinterpret_cast<const uint4 *>(rec + j)[0];
-        const uint2 b = reinterpret_cast<const uint2 *>(rec + j)[2];
-        uint4 o; o.x = blk; o.y = (uint32_t)d0; o.z = (uint32_t)d1; o.w = (uint32_t)d2;
-        *reinterpret_cast<uint4 *>(pre + j) = o;
-        blk += a.z; d0 += (int32_t)a.w; d1 += (int32_t)b.x; d2 += (int32_t)b.y;
+        if (k < n) t[k] = make_uint4(run.x + x.x - v.x, run.y + x.y - v.y, run.z + x.z - v.z, run.w + x.w - v.w);
+        run.x += __shfl_sync(0xFFFFFFFFu, x.x, 31); run.y += __shfl_sync(0xFFFFFFFFu, x.y, 31);
+        run.z += __shfl_sync(0xFFFFFFFFu, x.z, 31); run.w += __shfl_sync(0xFFFFFFFFu, x.w, 31);
     }
 }
 
@@ -1770,6 +1885,8 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sync_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sync_walk_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_idct_csc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
@@ -1816,12 +1933,20 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
     const uint32_t n = r.scta1 - r.scta0, ni = r.simg1 - r.simg0;
     if (n == 0 || ni == 0) return;
     const size_t lut_bytes = (size_t)a.max_lut_len * 2;
-    for (uint32_t round = 0; round <= (uint32_t)kSyncRounds; round++)
-        k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_stats);
-    k_sync_sweep<<<ni, 32, lut_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.stamps, (uint32_t)kSyncRounds, a.sync_stats);
-    k_sync_scan<<<ni, 256, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.recs, a.pres);
+    cudaMemsetAsync(a.sync_cnt, 0, 4 * 8, s);   // per launch sequence: the counters also index the work lists
+    // rounds 0 and 1 over all sub-sequences, rounds 2.. over the work list of the round before (lists alternate)
+    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, 0u, a.sync_cnt, a.sync_list[1]);
+    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, 1u, a.sync_cnt, a.sync_list[1]);
+    const uint32_t list_ctas = n < 592u ? n : 592u;   // 4 CTAs per SM walk the list with a grid stride
+    for (uint32_t round = 2; round <= (uint32_t)kSyncRounds; round++)
+        k_sync_walk_list<<<list_ctas, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_cnt,
+                                                                    a.sync_list[(round - 1u) & 1u], a.sync_list[round & 1u]);
+    k_sync_sweep<<<ni, kSweepThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.stamps, (uint32_t)kSyncRounds,
+                                                      a.sync_cnt, a.sync_stats);
+    k_sync_cta_totals<<<n, kHuffThreads, 0, s>>>(a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.recs, a.sync_cta_base + r.scta0);
+    k_sync_cta_scan<<<ni, 32, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.sync_cta_base + r.scta0, r.scta0);
     k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
-                                                                                           a.clean_len, a.luts, a.coef, a.status, a.recs, a.pres);
+                                                                                           a.clean_len, a.luts, a.coef, a.status, a.recs, a.sync_cta_base + r.scta0);
 }
 
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)

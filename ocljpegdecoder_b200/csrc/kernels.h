@@ -29,9 +29,11 @@ struct DecodeArgs
     uint64_t *chunk_state;   // single-pass pre-pass: look-back words, zeroed before every decode
     uint32_t *clean_len, *seg_start;
     SubRec *recs;       // self-synchronising path: one record per sub-sequence
-    SubPre *pres;
+    uint4 *sync_cta_base;   // per decode CTA of the self-synchronising path: (blocks started, DC sums) in front of it
     uint32_t *stamps;
     uint32_t *sync_stats;   // [r] = exit states changed in round r, [7] = sub-sequences re-walked by the sweep
+    uint32_t *sync_cnt;     // the same counters for the launch sequence in flight: they index the work lists
+    uint2 *sync_list[2];    // work lists of the rounds >= 2 (image, sub-sequence), written by one round, read by the next
     // outputs
     int16_t *coef;
     uint8_t *pixels;
@@ -52,8 +54,8 @@ cudaError_t configure_kernels(uint32_t max_lut_len);
 size_t huff_smem_bytes(uint32_t max_lut_len, bool ring);
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
-void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // kSyncRounds + 4 kernels
-constexpr int kSyncLaunches = kSyncRounds + 4;
+void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // kSyncRounds + 5 kernels
+constexpr int kSyncLaunches = kSyncRounds + 5;
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s);      // 1 kernel
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s);
 

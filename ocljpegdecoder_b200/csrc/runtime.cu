@@ -111,7 +111,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state, off_sync_cnt, off_sync_list;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -330,6 +330,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         {
             // no restart markers: self-synchronising sub-sequence decode, one lane per kSubBytes of stream
             im.sub_first = sub_total;
+            im.scta_first = (uint32_t)sctas.size();
             im.n_sub_max = (im.raw_len + kSubBytes - 1) / kSubBytes;
             if (im.n_sub_max == 0) im.n_sub_max = 1;
             sub_total += im.n_sub_max;
@@ -443,9 +444,11 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_seg_start = place(4 * (size_t)seg_total);
     b->off_status = place(4 * (size_t)n);
     b->off_recs = place(sizeof(SubRec) * (size_t)sub_total);
-    b->off_pres = place(sizeof(SubPre) * (size_t)sub_total);
+    b->off_pres = place(sizeof(uint4) * (sctas.size() + 1));
     b->off_stamps = place(4 * (size_t)sub_total);
     b->off_sync_stats = place(4 * 8);
+    b->off_sync_cnt = place(4 * 8);
+    b->off_sync_list = place(2 * sizeof(uint2) * (size_t)sub_total);
     b->off_chunk_state = place(8 * chunk_img.size());
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
@@ -497,9 +500,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.sync_ctas = reinterpret_cast<const HuffCtaDev *>(b->d_blob + b->off_sctas);
     a.sync_imgs = reinterpret_cast<const uint32_t *>(b->d_blob + b->off_simgs);
     a.recs = reinterpret_cast<SubRec *>(b->d_scratch + b->off_recs);
-    a.pres = reinterpret_cast<SubPre *>(b->d_scratch + b->off_pres);
+    a.sync_cta_base = reinterpret_cast<uint4 *>(b->d_scratch + b->off_pres);
     a.stamps = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_stamps);
     a.sync_stats = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_stats);
+    a.sync_cnt = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_cnt);
+    a.sync_list[0] = reinterpret_cast<uint2 *>(b->d_scratch + b->off_sync_list);
+    a.sync_list[1] = a.sync_list[0] + sub_total;
     a.tiles = reinterpret_cast<const TileDev *>(b->d_blob + b->off_tiles);
     a.luts = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_luts);
     a.qtabs = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_qtabs);
