@@ -1121,11 +1121,18 @@ __device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict
         br.bitpos += p & 7u;
         const uint32_t p_byte = p & ~7u;
         uint32_t comp = c < ny ? 0u : (c - ny + 1u);
-        uint32_t tab = sm_lut + 2u * (uint32_t)s_lut[(z == 0u ? 0u : 3u) + comp];
+        // The loop body is one straight path for DC and AC symbols alike (selects instead of branches): the lanes
+        // of a warp sit at unrelated places of their blocks, and a branch taken by a few lanes costs every lane.
+        // Table addresses of the three components, DC in the low half-word, AC in the high one.
+        const uint32_t t0 = (uint32_t)s_lut[0] | ((uint32_t)s_lut[3] << 16), t1 = (uint32_t)s_lut[1] | ((uint32_t)s_lut[4] << 16),
+                       t2 = (uint32_t)s_lut[2] | ((uint32_t)s_lut[5] << 16);
         while (p < limit)
         {
             const uint32_t pk = br.peek();
-            const uint32_t bits = z == 0u ? (uint32_t)kLutBitsDc : (uint32_t)kLutBits;
+            const bool dc = z == 0u;
+            const uint32_t tc = comp == 0u ? t0 : (comp == 1u ? t1 : t2);
+            const uint32_t tab = sm_lut + 2u * (dc ? (tc & 0xFFFFu) : (tc >> 16));
+            const uint32_t bits = dc ? (uint32_t)kLutBitsDc : (uint32_t)kLutBits;
             uint32_t e = lut_first(tab, pk, bits);
             if (!(e & 32u))
             {
@@ -1133,33 +1140,26 @@ __device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict
                 if (!(e & 32u)) { bad = true; break; }
             }
             const uint32_t len = e & 31u;
-            uint32_t size;
-            if (z == 0u)
-            {
-                size = (e >> 6) & 31u;
-                // DC code: a block starts here
-                if (r.fs == kSubNone) { r.fs = p; r.fc = c; }
-                r.nblk++;
-                const int32_t diff = extend_sz(pk << len, size);
-                if (comp == 0u) r.dc0 += diff; else if (comp == 1u) r.dc1 += diff; else r.dc2 += diff;
-                z = 1u;
-                tab = sm_lut + 2u * (uint32_t)s_lut[3u + comp];
-            }
-            else
-            {
-                size = (e >> 6) & 15u;
-                z += (e >> 10) + 1u;          // zero run + the coefficient (or the extra zero of a size-0 run); EOB: run 63
-            }
+            const uint32_t size = (e >> 6) & (dc ? 31u : 15u);
+            // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
+            // (a warp-vote guard around this was measured: slower at every quality)
+            const int32_t diff = dc ? extend_sz(pk << len, size) : 0;
+            const bool first = dc && r.fs == kSubNone;
+            r.fs = first ? p : r.fs;
+            r.fc = first ? c : r.fc;
+            r.nblk += dc ? 1u : 0u;
+            r.dc0 += comp == 0u ? diff : 0;
+            r.dc1 += comp == 1u ? diff : 0;
+            r.dc2 += comp == 2u ? diff : 0;
+            z = dc ? 1u : z + (e >> 10) + 1u;   // AC: zero run + the coefficient (or the extra zero of a size-0 run); EOB: run 63
             br.bitpos += len + size;
             br.refill();
             p = p_byte + br.nref * 32u + br.bitpos - bit0;
-            if (z >= 64u)
-            {
-                z = 0u;
-                c = (c + 1u == tot) ? 0u : c + 1u;
-                comp = c < ny ? 0u : (c - ny + 1u);
-                tab = sm_lut + 2u * (uint32_t)s_lut[comp];
-            }
+            const bool done = z >= 64u;         // the block is complete: next block of the MCU
+            z = done ? 0u : z;
+            const uint32_t cn = (c + 1u == tot) ? 0u : c + 1u;
+            c = done ? cn : c;
+            comp = c < ny ? 0u : (c - ny + 1u);
         }
     }
     // A non-code can only be met by a walk that started from a wrong guess (or in a corrupt stream, which
