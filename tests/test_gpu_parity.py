@@ -265,6 +265,41 @@ def test_other_baseline_configs(decoder, oracle, cfg, count):
         oracle.set_strict(True)
 
 
+@pytest.mark.parametrize("cfg,count,stride", [(2, 64, 7), (4, 8192, 61)])
+def test_full_size_selfsync_configs(decoder, oracle, cfg, count, stride):
+    """BASELINE configs[2] and configs[4] at full size (64 x 4K 4:4:4 q95, 8192 x 500x375 4:2:0 q75; no restart
+    markers: the self-synchronising path). Whole batch: clean status; on every `stride`-th image: the pixel
+    checksum is stable over repeated decodes and equals the checksum of the same image decoded in a small
+    batch of its own; on a sample: coefficients and pixels equal the oracle's."""
+    files = synth.config_batch(cfg, count)
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    stats = batch.sync_stats()
+    print("config", cfg, "sync stats", stats.tolist())
+    idx = list(range(0, count, stride))
+    sums = [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in idx]
+    batch.decode_steps(2)
+    assert not batch.status().any()
+    assert sums == [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in idx]
+    oracle.set_strict(False)
+    try:
+        for i in (0, idx[len(idx) // 2], count - 1):
+            rc, _, coef, bgra = oracle.decode(files[i])
+            assert rc == 0
+            assert np.array_equal(batch.coefs(i), coef)
+            _check_pixels(batch.pixels(i), bgra)
+    finally:
+        oracle.set_strict(True)
+    batch.close()
+    some = idx[::max(1, len(idx) // 6)]
+    st, _, pix = _decode(decoder, [files[k] for k in some])
+    assert not st.any()
+    for k, p in zip(some, pix):
+        assert hashlib.sha256(p.tobytes()).hexdigest() == sums[idx.index(k)]
+
+
 def test_selfsync_streams_without_restart_markers(decoder, oracle):
     """Streams without DRI take the self-synchronising sub-sequence decoder: quality 100 makes blocks that
     are longer than a whole 1024-bit sub-sequence, quality 5 makes sub-sequences with dozens of blocks."""
