@@ -85,6 +85,9 @@ struct SubRec
     uint32_t fs;        // bit position of the first of those blocks (kSubNone: none)
     uint32_t fc;        // its block-in-MCU index
 };
+// Checkpoint of round 0 at the middle of a sub-sequence, same layout as SubRec: p / cz = the state at the first
+// symbol at or behind the middle, the other fields = what the second half contributes.
+struct SubMid { uint32_t p, cz, nblk; int32_t dc[3]; uint32_t fs, fc; };
 struct SubPre { uint32_t blk; int32_t dc[3]; };   // exclusive prefix over the sub-sequences of one image (formed inside the decode CTA)
 constexpr uint32_t kSubInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kSubNone = 0xFFFFFFFFu;

@@ -1188,13 +1188,19 @@ __device__ __forceinline__ void sync_flag_changed(uint32_t img, uint32_t k, uint
     if (round == last_round) stamp[k] = round;          // what the sequential sweep repairs
 }
 
-// Rounds 0 and 1, one lane per sub-sequence. round 0: lane j walks sub-sequence j from the guessed state.
-// round 1: lane j walks sub-sequence j+1 from the exit state recorded for j; where that replaces a different
-// exit state, sub-sequence j+1 goes on the work list of round 2.
+// Rounds 0 and 1, one lane per sub-sequence.
+// round 0: lane j walks sub-sequence j from the guessed state, in two halves: the state at the first symbol at or
+//          behind the middle of the sub-sequence and what the second half contributes are kept as a checkpoint.
+// round 1: lane j walks sub-sequence j+1 from the exit state recorded for j, but only up to the middle. A decoder
+//          that started from a wrong guess falls into step with the true one within a few dozen symbols, so nearly
+//          always the lane arrives at exactly the checkpointed state: the second half of round 0 stands, the record
+//          is the lane's first half plus the checkpoint's second half and the exit state does not change. A lane
+//          that does not meet the checkpoint puts its sub-sequence on the work list of round 2 (full walk).
+// Half a pass over the stream instead of a whole one for round 1.
 __global__ void __launch_bounds__(kHuffThreads)
 k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
-            uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ cnt, uint2 *__restrict__ out_list)
+            SubMid *__restrict__ mids, uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ cnt, uint2 *__restrict__ out_list)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
@@ -1216,22 +1222,48 @@ k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, 
     SubRec *rec = recs + im.sub_first;
     uint32_t *stamp = stamps + im.sub_first;
     const uint8_t *base = clean + im.raw_off;
+    SubMid *mid = mids + im.sub_first;
     if (round == 0u)
     {
         if (j >= n_sub) return;
-        const WalkState s = {j * (uint32_t)(kSubBytes * 8), 0u, 0u};
-        const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((j + 1u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
+        const uint32_t lo = j * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
+        const WalkState s = {lo, 0u, 0u};
+        const WalkResult ra = walk_subsequence(base, sm_lut, s_lut, s, md, im.tot_blks, im.ny_blks);
+        const WalkState sm = {ra.p, ra.cz & 0xFFu, ra.cz >> 8};
+        const WalkResult rb = walk_subsequence(base, sm_lut, s_lut, sm, hi, im.tot_blks, im.ny_blks);
+        WalkResult r = rb;   // exit state of the second half
+        r.nblk = ra.nblk + rb.nblk; r.dc0 = ra.dc0 + rb.dc0; r.dc1 = ra.dc1 + rb.dc1; r.dc2 = ra.dc2 + rb.dc2;
+        if (ra.fs != kSubNone) { r.fs = ra.fs; r.fc = ra.fc; }
         store_rec(rec + j, r);
+        WalkResult m = rb;   // checkpoint: state at the middle + the second half's contribution
+        m.p = ra.p; m.cz = ra.cz;
+        store_rec(reinterpret_cast<SubRec *>(mid + j), m);
         stamp[j] = 0u;
         return;
     }
     if (j + 1u >= n_sub) return;
     const uint2 in = *reinterpret_cast<const uint2 *>(rec + j);
-    const uint2 old = *reinterpret_cast<const uint2 *>(rec + j + 1);
+    const uint32_t lo = (j + 1u) * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
     const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-    const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((j + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
-    store_rec(rec + j + 1, r);
-    if (r.p != old.x || r.cz != old.y) sync_flag_changed(cta.img, j + 1u, round, (uint32_t)kSyncRounds, cnt, out_list, stamp);
+    const WalkResult ra = walk_subsequence(base, sm_lut, s_lut, s, md, im.tot_blks, im.ny_blks);
+    const uint4 m0 = reinterpret_cast<const uint4 *>(mid + j + 1)[0];   // p, cz, nblk, dc0 of the checkpoint
+    if (ra.p == m0.x && ra.cz == m0.y)
+    {
+        const uint4 m1 = reinterpret_cast<const uint4 *>(mid + j + 1)[1];   // dc1, dc2, fs, fc
+        const uint2 ex = *reinterpret_cast<const uint2 *>(rec + j + 1);      // exit state: stands
+        WalkResult r;
+        r.p = ex.x; r.cz = ex.y;
+        r.nblk = ra.nblk + m0.z; r.dc0 = ra.dc0 + (int32_t)m0.w; r.dc1 = ra.dc1 + (int32_t)m1.x; r.dc2 = ra.dc2 + (int32_t)m1.y;
+        r.fs = ra.fs != kSubNone ? ra.fs : m1.z;
+        r.fc = ra.fs != kSubNone ? ra.fc : m1.w;
+        store_rec(rec + j + 1, r);
+    }
+    else
+    {
+        // not in step at the middle: full walk of sub-sequence j+1 in round 2 (entry j = "walk j+1 from the record of j")
+        const uint32_t slot = atomicAdd(&cnt[round], 1u);
+        out_list[slot] = make_uint2(cta.img, j);
+    }
 }
 
 // Rounds >= 2 touch few sub-sequences, scattered over the whole batch: they run over the compact work list
@@ -1935,8 +1967,8 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
     const size_t lut_bytes = (size_t)a.max_lut_len * 2;
     cudaMemsetAsync(a.sync_cnt, 0, 4 * 8, s);   // per launch sequence: the counters also index the work lists
     // rounds 0 and 1 over all sub-sequences, rounds 2.. over the work list of the round before (lists alternate)
-    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, 0u, a.sync_cnt, a.sync_list[1]);
-    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.stamps, 1u, a.sync_cnt, a.sync_list[1]);
+    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.mids, a.stamps, 0u, a.sync_cnt, a.sync_list[1]);
+    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.mids, a.stamps, 1u, a.sync_cnt, a.sync_list[1]);
     const uint32_t list_ctas = n < 592u ? n : 592u;   // 4 CTAs per SM walk the list with a grid stride
     for (uint32_t round = 2; round <= (uint32_t)kSyncRounds; round++)
         k_sync_walk_list<<<list_ctas, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_cnt,

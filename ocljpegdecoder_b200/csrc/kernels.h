@@ -29,6 +29,7 @@ struct DecodeArgs
     uint64_t *chunk_state;   // single-pass pre-pass: look-back words, zeroed before every decode
     uint32_t *clean_len, *seg_start;
     SubRec *recs;       // self-synchronising path: one record per sub-sequence
+    SubMid *mids;       // round-0 checkpoints at the middle of every sub-sequence
     uint4 *sync_cta_base;   // per decode CTA of the self-synchronising path: (blocks started, DC sums) in front of it
     uint32_t *stamps;
     uint32_t *sync_stats;   // [r] = exit states changed in round r, [7] = sub-sequences re-walked by the sweep

@@ -111,7 +111,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state, off_sync_cnt, off_sync_list;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state, off_sync_cnt, off_sync_list, off_mids;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -448,6 +448,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_stamps = place(4 * (size_t)sub_total);
     b->off_sync_stats = place(4 * 8);
     b->off_sync_cnt = place(4 * 8);
+    b->off_mids = place(sizeof(SubMid) * (size_t)sub_total);
     b->off_sync_list = place(2 * sizeof(uint2) * (size_t)sub_total);
     b->off_chunk_state = place(8 * chunk_img.size());
     b->scratch_bytes = off;
@@ -504,6 +505,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.stamps = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_stamps);
     a.sync_stats = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_stats);
     a.sync_cnt = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_cnt);
+    a.mids = reinterpret_cast<SubMid *>(b->d_scratch + b->off_mids);
     a.sync_list[0] = reinterpret_cast<uint2 *>(b->d_scratch + b->off_sync_list);
     a.sync_list[1] = a.sync_list[0] + sub_total;
     a.tiles = reinterpret_cast<const TileDev *>(b->d_blob + b->off_tiles);
