@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define B2J_ABI_VERSION 1
+#define B2J_ABI_VERSION 2
 
 /* ---- return codes (0 = success, like the reference's `true`) ---- */
 #define B2J_OK 0
@@ -74,6 +74,11 @@ extern "C" {
  * stops at them), fill FFs before a marker are skipped, tables may be redefined, 16-bit DQT entries are
  * read big-endian as the standard says (parser.cpp:81-87 does not swap). */
 #define B2J_PARSE_ROBUST 2
+
+/* ---- layout of the decoded pixels on the device (b2j_batch_set_output_format) ---- */
+#define B2J_OUT_BGRA 0       /* the reference's pixels: B,G,R,0 per pixel, pitch W*4 (oclDCT8x8.cpp:196, macro.h:141-145) */
+#define B2J_OUT_RGB24 1      /* R,G,B bytes interleaved, pitch W*3 (what image consumers want)     */
+#define B2J_OUT_RGB_PLANAR 2 /* three planes R, G, B of W*H bytes each (a CHW uint8 tensor left on the device)          */
 
 /* reference enum ColorSpace (macro.h:114-119) */
 #define B2J_CS_YUV444 0
@@ -169,6 +174,11 @@ int b2j_batch_decode_timed(b2j_batch *batch, void *stream, b2j_stage_times *time
 int b2j_batch_decode_steps(b2j_batch *batch, void *stream, int steps, b2j_stage_times *per_step, float *total_ms);
 int b2j_batch_sync(b2j_batch *batch, void *stream);
 
+/* Layout of the pixel plane for the decodes that follow (B2J_OUT_*; default B2J_OUT_BGRA). The values are the same
+ * in every format -- exact integer colour of decoder.cpp:367-370 -- only their arrangement differs. b2j_decode_host()
+ * and the reference-API shim always produce the reference's BGRA. */
+int b2j_batch_set_output_format(b2j_batch *batch, int format);
+
 /* Per-image status words (B2J_ST_* bits). Synchronises the stream. */
 int b2j_batch_status(b2j_batch *batch, void *stream, int32_t *status /* n */);
 
@@ -177,13 +187,13 @@ int b2j_batch_status(b2j_batch *batch, void *stream, int32_t *status /* n */);
  * sub-sequences the sequential sweep had to re-walk. Synchronises. */
 int b2j_batch_sync_stats(b2j_batch *batch, void *stream, uint32_t *out8);
 
-/* Device-resident results. Pixels: BGRA (A = 0), top-down, tight pitch width*4. */
+/* Device-resident results. Pixels: top-down, tight pitch, in the batch's output format (BGRA: width*4 per row, A = 0). */
 int b2j_batch_pixels_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes);
 /* Coefficient plane: int16[blk_count][64], natural order, QUANTISED (dequantisation happens
  * at IDCT load), MCU-interleaved block order. */
 int b2j_batch_coefs_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes);
 
-/* D2H of one image (synchronises). dst: width*height*4 bytes. */
+/* D2H of one image (synchronises). dst: width*height*4 bytes (BGRA) or width*height*3 (RGB24, planar RGB). */
 int b2j_batch_read_pixels(b2j_batch *batch, void *stream, int image, uint8_t *dst);
 /* D2H of every image into dsts[i] (pinned staging, one copy per image; synchronises). */
 int b2j_batch_read_all_pixels(b2j_batch *batch, void *stream, uint8_t *const *dsts);

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 GATE_REFERENCE = 0
 GATE_EXTENDED = 1
 PARSE_ROBUST = 2     # OR-able: skip COM / late APPn / unknown segments, big-endian 16-bit DQT
+OUT_BGRA, OUT_RGB24, OUT_RGB_PLANAR = 0, 1, 2
 
 B2J_OK = 0
 B2J_E_NODEVICE = -7
@@ -17,7 +18,7 @@ B2J_E_NODEVICE = -7
 EXPORTED_SYMBOLS = [
     "b2j_abi_version", "b2j_strerror", "b2j_last_error", "b2j_parse_header", "b2j_device_count",
     "b2j_create", "b2j_destroy", "b2j_batch_create", "b2j_batch_destroy", "b2j_batch_get_info",
-    "b2j_batch_upload", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status", "b2j_batch_sync_stats",
+    "b2j_batch_upload", "b2j_batch_set_output_format", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status", "b2j_batch_sync_stats",
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
     "b2j_batch_read_coefs", "b2j_decode_host",
 ]
@@ -95,6 +96,7 @@ def load_library():
     L.b2j_batch_destroy.restype = None
     L.b2j_batch_get_info.argtypes = [vp, ctypes.POINTER(BatchInfo)]
     L.b2j_batch_upload.argtypes = [vp, vp]
+    L.b2j_batch_set_output_format.argtypes = [vp, ci]
     L.b2j_batch_decode.argtypes = [vp, vp]
     L.b2j_batch_decode_timed.argtypes = [vp, vp, ctypes.POINTER(StageTimes)]
     L.b2j_batch_decode_steps.argtypes = [vp, vp, ci, ctypes.POINTER(StageTimes), ctypes.POINTER(ctypes.c_float)]
@@ -231,9 +233,16 @@ class Batch:
         _check(self.lib.b2j_batch_sync_stats(self._h, stream, out.ctypes.data), "b2j_batch_sync_stats")
         return out
 
+    def set_output_format(self, fmt):
+        """OUT_BGRA (reference layout, default), OUT_RGB24 (H,W,3) or OUT_RGB_PLANAR (3,H,W) for the decodes that follow."""
+        _check(self.lib.b2j_batch_set_output_format(self._h, fmt), "b2j_batch_set_output_format")
+        self.out_format = fmt
+
     def pixels(self, i, stream=None):
         d = self.descs[i]
-        out = np.zeros((d.height, d.width, 4), np.uint8)
+        fmt = getattr(self, "out_format", OUT_BGRA)
+        shape = (d.height, d.width, 4) if fmt == OUT_BGRA else ((d.height, d.width, 3) if fmt == OUT_RGB24 else (3, d.height, d.width))
+        out = np.zeros(shape, np.uint8)
         _check(self.lib.b2j_batch_read_pixels(self._h, stream, i, out.ctypes.data), "b2j_batch_read_pixels")
         return out
 

@@ -1584,7 +1584,9 @@ __device__ __noinline__ uint32_t green_special(uint32_t yy, uint32_t cb, uint32_
 // Colour work of one 4-pixel column of the tile for row groups [rg0, rg1) (every layout has 8 row
 // groups per MCU: mcu_h / RV == 8); a work item is 4 pixels x RV rows (one chroma row). Consecutive
 // threads are consecutive along x, so every store instruction writes 512 contiguous bytes per warp.
-template <int RH, int RV>
+// FMT: B2J_OUT_BGRA (the reference's 32-bit pixels), B2J_OUT_RGB24 (R,G,B bytes interleaved, pitch 3W: three 32-bit
+// stores per thread, 384 contiguous bytes per warp) or B2J_OUT_RGB_PLANAR (three W x H planes: one 32-bit store per plane).
+template <int RH, int RV, int FMT>
 __device__ __forceinline__ void csc_column(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t col, uint32_t rg0, uint32_t rg1)
 {
     using G = TileGeom<RH, RV>;
@@ -1596,9 +1598,11 @@ __device__ __forceinline__ void csc_column(const uint8_t *__restrict__ s_tile, c
     const uint32_t px = mxy.x * G::mcu_w + xin;
     const uint32_t py_top = mxy.y * G::mcu_h;
     if (px >= width) return;
-    const bool vec_ok = (width & 3u) == 0u;   // then the 4-pixel group is whole and 16-byte aligned
-    const size_t pitch = (size_t)width * 4u;
-    uint8_t *dst = sd.pix + ((size_t)py_top * width + px) * 4u;
+    const bool vec_ok = (width & 3u) == 0u;   // then the 4-pixel group is whole and aligned (16 / 12 / 4 bytes)
+    constexpr uint32_t bpp = FMT == B2J_OUT_BGRA ? 4u : (FMT == B2J_OUT_RGB24 ? 3u : 1u);   // bytes per pixel in one plane
+    const size_t pitch = (size_t)width * bpp;
+    const size_t plane = (size_t)width * height;   // planar: distance between the R, G and B planes
+    uint8_t *dst = sd.pix + ((size_t)py_top * width + px) * bpp;
     const uint32_t row0 = m * G::tot;
     // shared-memory addresses: luma block column and chroma blocks of this thread never change
     const uint32_t ycol = (xin >> 3), yoff = (xin & 7u) * 2u;
@@ -1636,43 +1640,91 @@ __device__ __forceinline__ void csc_column(const uint8_t *__restrict__ s_tile, c
             const uint32_t srow = row0 + (yin >> 3) * G::yh + ycol;
             const uint2 yv = *reinterpret_cast<const uint2 *>(s_tile + srow * 128u + (((yin & 7u) ^ (srow & 7u)) << 4) + yoff);
             const uint32_t y2[2] = {yv.x, yv.y};
-            uint32_t out[4];
+            uint32_t R[2], Gc[2], B[2];   // two pixels each: value | value << 16
 #pragma unroll
             for (int h = 0; h < 2; h++)
             {
-                const uint32_t R = addclamp2(y2[h], ro[h]), B = addclamp2(y2[h], bo[h]);
-                uint32_t Gc = addclamp2(y2[h], go[h]);
+                R[h] = addclamp2(y2[h], ro[h]); B[h] = addclamp2(y2[h], bo[h]);
+                Gc[h] = addclamp2(y2[h], go[h]);
                 if (__builtin_expect(sp[h], 0))
-                    Gc = green_special(y2[h], RH == 2 ? cb2[h] * 0x10001u : cb2[h], RH == 2 ? cr2[h] * 0x10001u : cr2[h]);
-                const uint32_t bg = __byte_perm(B, Gc, 0x6240);     // B0 G0 B1 G1
-                out[2 * h + 0] = __byte_perm(bg, R, 0x5410);        // B0 G0 R0 0
-                out[2 * h + 1] = __byte_perm(bg, R, 0x7632);        // B1 G1 R1 0
+                    Gc[h] = green_special(y2[h], RH == 2 ? cb2[h] * 0x10001u : cb2[h], RH == 2 ? cr2[h] * 0x10001u : cr2[h]);
             }
             uint8_t *d = dst + (size_t)yin * pitch;
-            if (vec_ok)
-                *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
+            if (FMT == B2J_OUT_BGRA)
+            {
+                uint32_t out[4];
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                {
+                    const uint32_t bg = __byte_perm(B[h], Gc[h], 0x6240);     // B0 G0 B1 G1
+                    out[2 * h + 0] = __byte_perm(bg, R[h], 0x5410);           // B0 G0 R0 0
+                    out[2 * h + 1] = __byte_perm(bg, R[h], 0x7632);           // B1 G1 R1 0
+                }
+                if (vec_ok)
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (px + k < width) reinterpret_cast<uint32_t *>(d)[k] = out[k];
+                }
+            }
+            else if (FMT == B2J_OUT_RGB24)
+            {
+                const uint32_t t0 = __byte_perm(R[0], Gc[0], 0x6240);         // R0 G0 R1 G1
+                const uint32_t t1 = __byte_perm(R[1], Gc[1], 0x6240);         // R2 G2 R3 G3
+                const uint32_t w0 = __byte_perm(t0, B[0], 0x2410);            // R0 G0 B0 R1
+                const uint32_t u = __byte_perm(t0, B[0], 0x0063);             // G1 B1 . .
+                const uint32_t w1 = __byte_perm(u, t1, 0x5410);               // G1 B1 R2 G2
+                const uint32_t w2 = __byte_perm(t1, B[1], 0x6324);            // B2 R3 G3 B3
+                if (vec_ok)
+                {
+                    uint32_t *dw = reinterpret_cast<uint32_t *>(d);
+                    dw[0] = w0; dw[1] = w1; dw[2] = w2;
+                }
+                else
+                {
+                    const uint32_t w[3] = {w0, w1, w2};
+#pragma unroll
+                    for (int k = 0; k < 12; k++)
+                        if (px + k / 3 < width) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                }
+            }
             else
             {
+                const uint32_t pr = __byte_perm(R[0], R[1], 0x6420), pg = __byte_perm(Gc[0], Gc[1], 0x6420), pb = __byte_perm(B[0], B[1], 0x6420);
+                if (vec_ok)
+                {
+                    *reinterpret_cast<uint32_t *>(d) = pr;
+                    *reinterpret_cast<uint32_t *>(d + plane) = pg;
+                    *reinterpret_cast<uint32_t *>(d + 2 * plane) = pb;
+                }
+                else
+                {
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (px + k < width) reinterpret_cast<uint32_t *>(d)[k] = out[k];
+                    for (int k = 0; k < 4; k++)
+                        if (px + k < width)
+                        {
+                            d[k] = (uint8_t)(pr >> (8 * k)); d[plane + k] = (uint8_t)(pg >> (8 * k)); d[2 * plane + k] = (uint8_t)(pb >> (8 * k));
+                        }
+                }
             }
         }
     }
 }
 
 // Colour phase: the tile's (columns x 8 row groups) work items spread evenly over all 192 threads.
-template <int RH, int RV>
+template <int RH, int RV, int FMT>
 __device__ __forceinline__ void csc_phase(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t tid)
 {
     using G = TileGeom<RH, RV>;
-    if (G::cols == 192) csc_column<RH, RV>(s_tile, sd, tid, 0, 8);                                  // 4:2:2: 8 items each
-    else if (G::cols == 96) csc_column<RH, RV>(s_tile, sd, tid % 96u, (tid / 96u) * 4u, (tid / 96u) * 4u + 4u);   // 4:4:0: 4 each
-    else if (tid < 128) csc_column<RH, RV>(s_tile, sd, tid, 0, 5);                                  // 128 columns: 5 items ...
+    if (G::cols == 192) csc_column<RH, RV, FMT>(s_tile, sd, tid, 0, 8);                                  // 4:2:2: 8 items each
+    else if (G::cols == 96) csc_column<RH, RV, FMT>(s_tile, sd, tid % 96u, (tid / 96u) * 4u, (tid / 96u) * 4u + 4u);   // 4:4:0: 4 each
+    else if (tid < 128) csc_column<RH, RV, FMT>(s_tile, sd, tid, 0, 5);                                  // 128 columns: 5 items ...
     else
     {
-        csc_column<RH, RV>(s_tile, sd, tid - 128u, 5, 8);                                           // ... or 2 x 3 items
-        csc_column<RH, RV>(s_tile, sd, tid - 64u, 5, 8);
+        csc_column<RH, RV, FMT>(s_tile, sd, tid - 128u, 5, 8);                                           // ... or 2 x 3 items
+        csc_column<RH, RV, FMT>(s_tile, sd, tid - 64u, 5, 8);
     }
 }
 
@@ -1777,15 +1829,16 @@ __device__ __forceinline__ void idct_dispatch(uint8_t *tilep, const TileSide &sd
 }
 
 // chroma replication + colour + store (decoder.cpp:443-495, 367-370)
+template <int FMT>
 __device__ __forceinline__ void csc_dispatch(const uint8_t *tilep, const TileSide &sd)
 {
     const uint32_t tid = threadIdx.x;
     switch (sd.mode)
     {
-    case kMode444: csc_phase<1, 1>(tilep, sd, tid); break;
-    case kMode420: csc_phase<2, 2>(tilep, sd, tid); break;
-    case kMode422: csc_phase<2, 1>(tilep, sd, tid); break;
-    default:       csc_phase<1, 2>(tilep, sd, tid); break;
+    case kMode444: csc_phase<1, 1, FMT>(tilep, sd, tid); break;
+    case kMode420: csc_phase<2, 2, FMT>(tilep, sd, tid); break;
+    case kMode422: csc_phase<2, 1, FMT>(tilep, sd, tid); break;
+    default:       csc_phase<1, 2, FMT>(tilep, sd, tid); break;
     }
 }
 
@@ -1841,7 +1894,7 @@ __device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMo
 #ifndef B2J_IDCT_MIN_CTAS
 #define B2J_IDCT_MIN_CTAS 5   // measured on B200: 64 registers with ~220 B of spills beats 80 registers at 4 CTAs per SM
 #endif
-template <bool USE_TMA, bool NARROWQ>
+template <bool USE_TMA, bool NARROWQ, int FMT>
 __global__ void __launch_bounds__(kTileBlocks, B2J_IDCT_MIN_CTAS)
 k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
            const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
@@ -1885,7 +1938,7 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
     }
     idct_dispatch<NARROWQ>(sm.tile[0], sm.side[0]);
     __syncthreads();
-    csc_dispatch(sm.tile[0], sm.side[0]);
+    csc_dispatch<FMT>(sm.tile[0], sm.side[0]);
 }
 
 // =====================================================================================
@@ -1921,13 +1974,15 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_idct_csc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+#define B2J_IDCT_ATTR(T, Q, F) \
+    e = cudaFuncSetAttribute(k_idct_csc<T, Q, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_idct_csc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_idct_csc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_idct_csc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    B2J_IDCT_ATTR(true, true, B2J_OUT_BGRA) B2J_IDCT_ATTR(true, false, B2J_OUT_BGRA)
+    B2J_IDCT_ATTR(false, true, B2J_OUT_BGRA) B2J_IDCT_ATTR(false, false, B2J_OUT_BGRA)
+    B2J_IDCT_ATTR(true, true, B2J_OUT_RGB24) B2J_IDCT_ATTR(true, false, B2J_OUT_RGB24)
+    B2J_IDCT_ATTR(true, true, B2J_OUT_RGB_PLANAR) B2J_IDCT_ATTR(true, false, B2J_OUT_RGB_PLANAR)
+#undef B2J_IDCT_ATTR
+    return cudaSuccess;
 }
 
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
@@ -1985,9 +2040,12 @@ void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.tile1 - r.tile0;
     if (n == 0) return;
-#define B2J_IDCT_LAUNCH(T, Q) k_idct_csc<T, Q><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status)
-    if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false); else B2J_IDCT_LAUNCH(true, true); }
-    else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false); else B2J_IDCT_LAUNCH(false, true); }
+#define B2J_IDCT_LAUNCH(T, Q, F) k_idct_csc<T, Q, F><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status)
+    // the other output formats exist for the TMA variant only (B2J_USE_TMA=0 is a measurement knob of the BGRA path)
+    if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24); }
+    else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR); }
+    else if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA); }
+    else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false, B2J_OUT_BGRA); else B2J_IDCT_LAUNCH(false, true, B2J_OUT_BGRA); }
 #undef B2J_IDCT_LAUNCH
 }
 

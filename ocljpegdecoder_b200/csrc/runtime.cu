@@ -529,6 +529,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.n_tiles = (uint32_t)tiles.size();
     a.max_lut_len = max_lut_len;
     a.use_tma = ctx->use_tma;
+    a.out_format = B2J_OUT_BGRA;
     a.any_wide_q = false;
     for (const ImgDev &im : b->imgs) a.any_wide_q = a.any_wide_q || im.wide_q != 0;
     {
@@ -718,11 +719,23 @@ extern "C" int b2j_batch_sync_stats(b2j_batch *b, void *stream, uint32_t *out8)
     return B2J_OK;
 }
 
+static size_t image_bytes(const b2j_batch *b, const ImgDev &im)
+{
+    return (size_t)im.width * im.height * (b->args.out_format == B2J_OUT_BGRA ? 4u : 3u);
+}
+
+extern "C" int b2j_batch_set_output_format(b2j_batch *b, int format)
+{
+    if (!b || (format != B2J_OUT_BGRA && format != B2J_OUT_RGB24 && format != B2J_OUT_RGB_PLANAR)) return B2J_E_ARG;
+    b->args.out_format = format;   // the pixel plane is sized for 4 bytes per pixel: every format fits
+    return B2J_OK;
+}
+
 extern "C" int b2j_batch_pixels_device(const b2j_batch *b, int image, void **dptr, size_t *nbytes)
 {
     if (!b || image < 0 || image >= b->n || !dptr) return B2J_E_ARG;
     *dptr = b->d_pix + b->imgs[(size_t)image].pix_off;
-    if (nbytes) *nbytes = (size_t)b->imgs[(size_t)image].width * b->imgs[(size_t)image].height * 4;
+    if (nbytes) *nbytes = image_bytes(b, b->imgs[(size_t)image]);
     return B2J_OK;
 }
 
@@ -740,7 +753,7 @@ extern "C" int b2j_batch_read_pixels(b2j_batch *b, void *stream, int image, uint
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t s = pick_stream(b, stream);
     const ImgDev &im = b->imgs[(size_t)image];
-    CU_TRY(cudaMemcpyAsync(dst, b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(dst, b->d_pix + im.pix_off, image_bytes(b, im), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     return B2J_OK;
 }
@@ -754,7 +767,7 @@ extern "C" int b2j_batch_read_all_pixels(b2j_batch *b, void *stream, uint8_t *co
     {
         const ImgDev &im = b->imgs[(size_t)i];
         if (!dsts[i]) continue;
-        CU_TRY(cudaMemcpyAsync(dsts[i], b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(dsts[i], b->d_pix + im.pix_off, image_bytes(b, im), cudaMemcpyDeviceToHost, s));
     }
     CU_TRY(cudaStreamSynchronize(s));
     return B2J_OK;

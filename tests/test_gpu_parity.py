@@ -415,3 +415,56 @@ def test_kernel_variants_agree(decoder):
         for i in range(len(files)):
             assert np.array_equal(c[i], c0[i]), (name, i)
             assert np.array_equal(p[i], p0[i]), (name, i)
+
+
+def test_output_formats(decoder, oracle):
+    """RGB24 and planar RGB carry exactly the reference's colour values (decoder.cpp:367-370), rearranged: all
+    sampling layouts, widths that are and are not multiples of four, 16-bit quantisers (the generic kernel)."""
+    import ocljpegdecoder_b200 as b2j
+    specs = [(640, 480, "420", 90, 16), (200, 120, "444", 85, 0), (131, 77, "420", 75, 3), (322, 98, "422", 60, 5), (65, 33, "444", 95, 0)]
+    files = [synth.synth_jpeg(w, h, 700 + i, q, ss, ri) for i, (w, h, ss, q, ri) in enumerate(specs)]
+    files.append(_crafted((1, 2), 40, 48, 2, 0, seed=9, stuffed=True))
+    batch = decoder.batch(files)
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    bgra = [batch.pixels(i).copy() for i in range(len(files))]
+    for b in bgra:
+        assert not b[..., 3].any()
+    batch.set_output_format(b2j.OUT_RGB24)
+    batch.decode()
+    for i, b in enumerate(bgra):
+        rgb = batch.pixels(i)
+        assert rgb.shape == b.shape[:2] + (3,)
+        assert np.array_equal(rgb, b[..., 2::-1]), i
+    batch.set_output_format(b2j.OUT_RGB_PLANAR)
+    batch.decode()
+    for i, b in enumerate(bgra):
+        chw = batch.pixels(i)
+        assert chw.shape == (3,) + b.shape[:2]
+        assert np.array_equal(chw, np.moveaxis(b[..., 2::-1], 2, 0)), i
+    batch.set_output_format(b2j.OUT_BGRA)
+    batch.decode()
+    for i, b in enumerate(bgra):
+        assert np.array_equal(batch.pixels(i), b)
+    batch.close()
+    oracle.set_strict(False)
+    try:
+        rc, _, _, want = oracle.decode(files[2])
+    finally:
+        oracle.set_strict(True)
+    assert rc == 0 and np.array_equal(bgra[2], want)
+    # 16-bit DQT: the generic (non-dp2a) kernel variant
+    rng = np.random.RandomState(5)
+    blocks = np.zeros((2 * 6, 64), np.int64)
+    blocks[:, 0] = rng.randint(-20, 20, 12)
+    blocks[:, 1:4] = rng.randint(-2, 3, (12, 3))
+    wide = jpegcraft.build_jpeg(32, 16, (2, 2), blocks, [[(1 + (i % 3)) for i in range(64)], [2] * 64], dqt16=True)
+    b2 = decoder.batch([wide])
+    b2.upload()
+    b2.decode()
+    ref = b2.pixels(0).copy()
+    b2.set_output_format(b2j.OUT_RGB24)
+    b2.decode()
+    assert np.array_equal(b2.pixels(0), ref[..., 2::-1])
+    b2.close()
