@@ -5,7 +5,7 @@ import sys
 WANT = [
     'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-    'smsp__issue_active.avg.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
     'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
     'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
     'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
