@@ -74,6 +74,9 @@ extern "C" {
  * stops at them), fill FFs before a marker are skipped, tables may be redefined, 16-bit DQT entries are
  * read big-endian as the standard says (parser.cpp:81-87 does not swap). */
 #define B2J_PARSE_ROBUST 2
+/* OR-able: one-component (grayscale) baseline frames, which the reference refuses
+ * (parser.cpp:104-106, decoder.cpp:26-31). Decoded like the luma of a colour file with U = V = 0 in YUV_to_RGB32. */
+#define B2J_GATE_GRAY 4
 
 /* ---- layout of the decoded pixels on the device (b2j_batch_set_output_format) ---- */
 #define B2J_OUT_BGRA 0       /* the reference's pixels: B,G,R,0 per pixel, pitch W*4 (oclDCT8x8.cpp:196, macro.h:141-145) */
@@ -84,6 +87,7 @@ extern "C" {
 #define B2J_CS_YUV444 0
 #define B2J_CS_YUV411 1
 #define B2J_CS_OTHER 2
+#define B2J_CS_GRAY 3     /* not in the reference's enum: one component (B2J_GATE_GRAY) */
 
 /* Parsed frame/scan header of one baseline JPEG: the POD equivalent of the reference's
  * JPG_DATA (jpeg.h:59-81) minus the pointers. Quantisation tables stay in file (zig-zag)

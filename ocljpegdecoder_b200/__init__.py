@@ -7,5 +7,5 @@ fails, and if no B200 is visible, ``Decoder()`` raises.
 """
 from .api import (  # noqa: F401
     B2JError, BatchInfo, Decoder, Batch, ImageDesc, StageTimes, parse_header, library_path, load_library,
-    GATE_REFERENCE, GATE_EXTENDED, PARSE_ROBUST, OUT_BGRA, OUT_RGB24, OUT_RGB_PLANAR, EXPORTED_SYMBOLS,
+    GATE_REFERENCE, GATE_EXTENDED, PARSE_ROBUST, GATE_GRAY, OUT_BGRA, OUT_RGB24, OUT_RGB_PLANAR, EXPORTED_SYMBOLS,
 )

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 GATE_REFERENCE = 0
 GATE_EXTENDED = 1
 PARSE_ROBUST = 2     # OR-able: skip COM / late APPn / unknown segments, big-endian 16-bit DQT
+GATE_GRAY = 4        # OR-able: one-component (grayscale) frames
 OUT_BGRA, OUT_RGB24, OUT_RGB_PLANAR = 0, 1, 2
 
 B2J_OK = 0

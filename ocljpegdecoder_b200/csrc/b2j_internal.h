@@ -42,7 +42,7 @@ constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table
 
 // sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)
-enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3 };
+enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3, kModeGray = 4 };   // gray: one component
 
 // Per-image record in device memory.
 struct ImgDev

@@ -52,9 +52,20 @@ bool parse_dqt(b2j_image_desc &d, Reader &r, size_t len, bool robust)
 }
 
 // parser.cpp:102-130
-bool parse_sof0(b2j_image_desc &d, Reader &r, size_t len)
+bool parse_sof0(b2j_image_desc &d, Reader &r, size_t len, bool allow_gray)
 {
     uint8_t b[15];
+    if (allow_gray && len == 9)
+    {
+        // one-component frame (B2J_GATE_GRAY): a single 1x1-sampled component
+        if (!r.take(b, 9) || b[0] != 8 || b[5] != 1 || b[7] != 0x11) return false;
+        d.height = (int32_t)be16(b + 1);
+        d.width = (int32_t)be16(b + 3);
+        d.sampling[0] = 0x11; d.sampling[1] = d.sampling[2] = 0;
+        d.quant_id[0] = d.quant_id[1] = d.quant_id[2] = b[8];
+        d.color_space = B2J_CS_GRAY;
+        return true;
+    }
     if (len != sizeof(b) || !r.take(b, sizeof(b))) return false;
     if (b[0] != 8 || b[5] != 3) return false;
     d.height = (int32_t)be16(b + 1);
@@ -102,6 +113,13 @@ bool parse_dht(b2j_image_desc &d, Reader &r, size_t len, bool robust)
 bool parse_sos(b2j_image_desc &d, Reader &r, size_t len)
 {
     uint8_t b[10];
+    if (d.color_space == B2J_CS_GRAY)
+    {
+        if (len != 6 || !r.take(b, 6)) return false;
+        if (b[0] != 1 || b[3] != 0 || b[4] != 0x3F || b[5] != 0) return false;
+        d.huff_id[0] = d.huff_id[1] = d.huff_id[2] = b[2];
+        return true;
+    }
     if (len != sizeof(b) || !r.take(b, sizeof(b))) return false;
     if (b[0] != 3 || b[7] != 0 || b[8] != 0x3F || b[9] != 0) return false;
     for (int c = 0; c < 3; c++) d.huff_id[c] = b[1 + 2 * c + 1];
@@ -119,6 +137,7 @@ int check_gate(const b2j_image_desc &d, int gate)
         const int td = d.huff_id[c] >> 4, ta = d.huff_id[c] & 0xF;
         if (td > 3 || ta > 3 || !d.huff_present[td] || !d.huff_present[4 + ta]) return B2J_E_UNSUPPORTED;
     }
+    if (d.color_space == B2J_CS_GRAY) return B2J_OK;   // admitted by parse_sof0 under B2J_GATE_GRAY only
     if (d.sampling[1] != 0x11 || d.sampling[2] != 0x11) return B2J_E_UNSUPPORTED;
     const int y = d.sampling[0];
     if (y == 0x22 || y == 0x11) return B2J_OK;
@@ -145,7 +164,8 @@ void derive_geometry(b2j_image_desc &d)
     d.mcu_count_h = (d.height - 1) / d.mcu_height + 1;
     d.mcu_count = d.mcu_count_w * d.mcu_count_h;
     d.blk_count = d.mcu_count * d.tot_blks_per_mcu;
-    d.color_space = d.sampling[0] == 0x22 ? B2J_CS_YUV411 : (d.sampling[0] == 0x11 ? B2J_CS_YUV444 : B2J_CS_OTHER);
+    if (d.color_space != B2J_CS_GRAY)
+        d.color_space = d.sampling[0] == 0x22 ? B2J_CS_YUV411 : (d.sampling[0] == 0x11 ? B2J_CS_YUV444 : B2J_CS_OTHER);
 }
 
 } // namespace
@@ -155,6 +175,7 @@ extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate_flags,
     if (!file || !out) return B2J_E_ARG;
     const bool robust = (gate_flags & B2J_PARSE_ROBUST) != 0;
     const int gate = gate_flags & 1;
+    const bool allow_gray = (gate_flags & B2J_GATE_GRAY) != 0;
     b2j_image_desc &d = *out;
     memset(&d, 0, sizeof(d));
     Reader r{file, len, 0};
@@ -197,7 +218,7 @@ extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate_flags,
         switch (tag[1])
         {
         case 0xDB: if (!parse_dqt(d, r, seglen, robust)) return B2J_E_FORMAT; break;
-        case 0xC0: if (!parse_sof0(d, r, seglen)) return B2J_E_FORMAT; break;
+        case 0xC0: if (!parse_sof0(d, r, seglen, allow_gray)) return B2J_E_FORMAT; break;
         case 0xC4: if (!parse_dht(d, r, seglen, robust)) return B2J_E_FORMAT; break;
         case 0xDD:
             if (seglen != 2 || !r.take(lb, 2)) return B2J_E_FORMAT;   // parser.cpp:156-168

@@ -1532,7 +1532,7 @@ constexpr uint32_t kQtStride = 68;       // words between the per-component quan
 struct TileSide
 {
     alignas(16) uint32_t qt[3 * kQtStride];   // quantisers, natural order, widened to 32 bit
-    uint2 mcu_xy[kTileBlocks / 3];            // MCU coordinates inside the image
+    uint2 mcu_xy[kTileBlocks];                // MCU coordinates inside the image (up to 192 one-block MCUs of a gray image)
     uint8_t *pix;                             // first byte of the image in the pixel plane
     uint32_t width, height;
     uint32_t mode, n_mcus;
@@ -1579,6 +1579,72 @@ __device__ __noinline__ uint32_t green_special(uint32_t yy, uint32_t cb, uint32_
     const uint32_t ga = clamp255(ya + csc_g_off_b(u0, v0) - csc_g_fix_b(ya, u0, v0));
     const uint32_t gb = clamp255(yb + csc_g_off_b(u1, v1) - csc_g_fix_b(yb, u1, v1));
     return ga | (gb << 16);
+}
+
+// Four pixels (two packed pairs per channel: value | value << 16) -> memory at d, in the output format FMT.
+template <int FMT>
+__device__ __forceinline__ void store_pixels4(uint8_t *__restrict__ d, size_t plane, uint32_t px, uint32_t width, bool vec_ok,
+                                              const uint32_t R[2], const uint32_t Gc[2], const uint32_t B[2])
+{
+    if (FMT == B2J_OUT_BGRA)
+    {
+        uint32_t out[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+            const uint32_t bg = __byte_perm(B[h], Gc[h], 0x6240);     // B0 G0 B1 G1
+            out[2 * h + 0] = __byte_perm(bg, R[h], 0x5410);           // B0 G0 R0 0
+            out[2 * h + 1] = __byte_perm(bg, R[h], 0x7632);           // B1 G1 R1 0
+        }
+        if (vec_ok)
+            *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (px + k < width) reinterpret_cast<uint32_t *>(d)[k] = out[k];
+        }
+    }
+    else if (FMT == B2J_OUT_RGB24)
+    {
+        const uint32_t t0 = __byte_perm(R[0], Gc[0], 0x6240);         // R0 G0 R1 G1
+        const uint32_t t1 = __byte_perm(R[1], Gc[1], 0x6240);         // R2 G2 R3 G3
+        const uint32_t w0 = __byte_perm(t0, B[0], 0x2410);            // R0 G0 B0 R1
+        const uint32_t u = __byte_perm(t0, B[0], 0x0063);             // G1 B1 . .
+        const uint32_t w1 = __byte_perm(u, t1, 0x5410);               // G1 B1 R2 G2
+        const uint32_t w2 = __byte_perm(t1, B[1], 0x6324);            // B2 R3 G3 B3
+        if (vec_ok)
+        {
+            uint32_t *dw = reinterpret_cast<uint32_t *>(d);
+            dw[0] = w0; dw[1] = w1; dw[2] = w2;
+        }
+        else
+        {
+            const uint32_t w[3] = {w0, w1, w2};
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (px + k / 3 < width) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+    else
+    {
+        const uint32_t pr = __byte_perm(R[0], R[1], 0x6420), pg = __byte_perm(Gc[0], Gc[1], 0x6420), pb = __byte_perm(B[0], B[1], 0x6420);
+        if (vec_ok)
+        {
+            *reinterpret_cast<uint32_t *>(d) = pr;
+            *reinterpret_cast<uint32_t *>(d + plane) = pg;
+            *reinterpret_cast<uint32_t *>(d + 2 * plane) = pb;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (px + k < width)
+                {
+                    d[k] = (uint8_t)(pr >> (8 * k)); d[plane + k] = (uint8_t)(pg >> (8 * k)); d[2 * plane + k] = (uint8_t)(pb >> (8 * k));
+                }
+        }
+    }
 }
 
 // Colour work of one 4-pixel column of the tile for row groups [rg0, rg1) (every layout has 8 row
@@ -1649,66 +1715,7 @@ __device__ __forceinline__ void csc_column(const uint8_t *__restrict__ s_tile, c
                 if (__builtin_expect(sp[h], 0))
                     Gc[h] = green_special(y2[h], RH == 2 ? cb2[h] * 0x10001u : cb2[h], RH == 2 ? cr2[h] * 0x10001u : cr2[h]);
             }
-            uint8_t *d = dst + (size_t)yin * pitch;
-            if (FMT == B2J_OUT_BGRA)
-            {
-                uint32_t out[4];
-#pragma unroll
-                for (int h = 0; h < 2; h++)
-                {
-                    const uint32_t bg = __byte_perm(B[h], Gc[h], 0x6240);     // B0 G0 B1 G1
-                    out[2 * h + 0] = __byte_perm(bg, R[h], 0x5410);           // B0 G0 R0 0
-                    out[2 * h + 1] = __byte_perm(bg, R[h], 0x7632);           // B1 G1 R1 0
-                }
-                if (vec_ok)
-                    *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
-                else
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (px + k < width) reinterpret_cast<uint32_t *>(d)[k] = out[k];
-                }
-            }
-            else if (FMT == B2J_OUT_RGB24)
-            {
-                const uint32_t t0 = __byte_perm(R[0], Gc[0], 0x6240);         // R0 G0 R1 G1
-                const uint32_t t1 = __byte_perm(R[1], Gc[1], 0x6240);         // R2 G2 R3 G3
-                const uint32_t w0 = __byte_perm(t0, B[0], 0x2410);            // R0 G0 B0 R1
-                const uint32_t u = __byte_perm(t0, B[0], 0x0063);             // G1 B1 . .
-                const uint32_t w1 = __byte_perm(u, t1, 0x5410);               // G1 B1 R2 G2
-                const uint32_t w2 = __byte_perm(t1, B[1], 0x6324);            // B2 R3 G3 B3
-                if (vec_ok)
-                {
-                    uint32_t *dw = reinterpret_cast<uint32_t *>(d);
-                    dw[0] = w0; dw[1] = w1; dw[2] = w2;
-                }
-                else
-                {
-                    const uint32_t w[3] = {w0, w1, w2};
-#pragma unroll
-                    for (int k = 0; k < 12; k++)
-                        if (px + k / 3 < width) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-                }
-            }
-            else
-            {
-                const uint32_t pr = __byte_perm(R[0], R[1], 0x6420), pg = __byte_perm(Gc[0], Gc[1], 0x6420), pb = __byte_perm(B[0], B[1], 0x6420);
-                if (vec_ok)
-                {
-                    *reinterpret_cast<uint32_t *>(d) = pr;
-                    *reinterpret_cast<uint32_t *>(d + plane) = pg;
-                    *reinterpret_cast<uint32_t *>(d + 2 * plane) = pb;
-                }
-                else
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (px + k < width)
-                        {
-                            d[k] = (uint8_t)(pr >> (8 * k)); d[plane + k] = (uint8_t)(pg >> (8 * k)); d[2 * plane + k] = (uint8_t)(pb >> (8 * k));
-                        }
-                }
-            }
+            store_pixels4<FMT>(dst + (size_t)yin * pitch, plane, px, width, vec_ok, R, Gc, B);
         }
     }
 }
@@ -1763,7 +1770,7 @@ __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const Ti
     using G = TileGeom<RH, RV>;
     const uint32_t tid = threadIdx.x;
     const uint32_t bi = tid % G::tot;
-    const uint32_t comp = bi < G::ny ? 0u : (bi - G::ny + 1u);
+    const uint32_t comp = RH == 0 ? 0u : (bi < G::ny ? 0u : (bi - G::ny + 1u));   // RH == 0: one-component image
     const uint32_t *q = sd.qt + comp * kQtStride;
     uint8_t *rowp = tilep + tid * 128u;
     const uint32_t sw = tid & 7u;
@@ -1829,6 +1836,33 @@ __device__ __forceinline__ void idct_dispatch(uint8_t *tilep, const TileSide &sd
 }
 
 // chroma replication + colour + store (decoder.cpp:443-495, 367-370)
+// One-component images (kModeGray): a tile is 192 one-block MCUs; an item is 4 pixels x 8 rows of one block.
+// YUV_to_RGB32 with U = V = 0 (decoder.cpp:367-370): R = G = B = clamp(Y + 128).
+template <int FMT>
+__device__ __forceinline__ void csc_gray(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t tid)
+{
+    const uint32_t width = sd.width, height = sd.height;
+    const bool vec_ok = (width & 3u) == 0u;
+    constexpr uint32_t bpp = FMT == B2J_OUT_BGRA ? 4u : (FMT == B2J_OUT_RGB24 ? 3u : 1u);
+    const size_t pitch = (size_t)width * bpp, plane = (size_t)width * height;
+    for (uint32_t it = tid; it < sd.n_mcus * 2u; it += kTileBlocks)
+    {
+        const uint32_t m = it >> 1, xin = (it & 1u) * 4u;
+        const uint2 mxy = sd.mcu_xy[m];
+        const uint32_t px = mxy.x * 8u + xin, py = mxy.y * 8u;
+        if (px >= width) continue;
+        uint8_t *dst = sd.pix + ((size_t)py * width + px) * bpp;
+#pragma unroll 1
+        for (uint32_t r = 0; r < 8u && py + r < height; r++)
+        {
+            const uint2 yv = *reinterpret_cast<const uint2 *>(s_tile + m * 128u + ((r ^ (m & 7u)) << 4) + xin * 2u);
+            // samples carry the +256 bias of the IDCT phase: Y + 128 = Yb - 128
+            const uint32_t g[2] = {addclamp2(yv.x, 0xFF80FF80u), addclamp2(yv.y, 0xFF80FF80u)};
+            store_pixels4<FMT>(dst + (size_t)r * pitch, plane, px, width, vec_ok, g, g, g);
+        }
+    }
+}
+
 template <int FMT>
 __device__ __forceinline__ void csc_dispatch(const uint8_t *tilep, const TileSide &sd)
 {
@@ -1894,7 +1928,10 @@ __device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMo
 #ifndef B2J_IDCT_MIN_CTAS
 #define B2J_IDCT_MIN_CTAS 5   // measured on B200: 64 registers with ~220 B of spills beats 80 registers at 4 CTAs per SM
 #endif
-template <bool USE_TMA, bool NARROWQ, int FMT>
+// GRAY: the kernel for the tiles of one-component images (B2J_GATE_GRAY). A kernel of its own over a tile range of
+// its own (the host sorts a part's tiles by kind), because merely carrying the extra paths, or a test for them at
+// the top of the kernel, slows the colour kernel down by 2 % (measured).
+template <bool USE_TMA, bool NARROWQ, int FMT, bool GRAY = false>
 __global__ void __launch_bounds__(kTileBlocks, B2J_IDCT_MIN_CTAS)
 k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
            const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
@@ -1936,9 +1973,18 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
         side_store<NARROWQ>(sm.side[0], d, r, pix);
         __syncthreads();
     }
-    idct_dispatch<NARROWQ>(sm.tile[0], sm.side[0]);
-    __syncthreads();
-    csc_dispatch<FMT>(sm.tile[0], sm.side[0]);
+    if (GRAY)
+    {
+        idct_phase<0, 0, NARROWQ>(sm.tile[0], sm.side[0]);
+        __syncthreads();
+        csc_gray<FMT>(sm.tile[0], sm.side[0], tid);
+    }
+    else
+    {
+        idct_dispatch<NARROWQ>(sm.tile[0], sm.side[0]);
+        __syncthreads();
+        csc_dispatch<FMT>(sm.tile[0], sm.side[0]);
+    }
 }
 
 // =====================================================================================
@@ -1981,6 +2027,12 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     B2J_IDCT_ATTR(false, true, B2J_OUT_BGRA) B2J_IDCT_ATTR(false, false, B2J_OUT_BGRA)
     B2J_IDCT_ATTR(true, true, B2J_OUT_RGB24) B2J_IDCT_ATTR(true, false, B2J_OUT_RGB24)
     B2J_IDCT_ATTR(true, true, B2J_OUT_RGB_PLANAR) B2J_IDCT_ATTR(true, false, B2J_OUT_RGB_PLANAR)
+#undef B2J_IDCT_ATTR
+#define B2J_IDCT_ATTR(Q, F) \
+    e = cudaFuncSetAttribute(k_idct_csc<true, Q, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
+    if (e != cudaSuccess) return e;
+    B2J_IDCT_ATTR(true, B2J_OUT_BGRA) B2J_IDCT_ATTR(false, B2J_OUT_BGRA) B2J_IDCT_ATTR(true, B2J_OUT_RGB24) B2J_IDCT_ATTR(false, B2J_OUT_RGB24)
+    B2J_IDCT_ATTR(true, B2J_OUT_RGB_PLANAR) B2J_IDCT_ATTR(false, B2J_OUT_RGB_PLANAR)
 #undef B2J_IDCT_ATTR
     return cudaSuccess;
 }
@@ -2038,14 +2090,23 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
 
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
-    const uint32_t n = r.tile1 - r.tile0;
-    if (n == 0) return;
-#define B2J_IDCT_LAUNCH(T, Q, F) k_idct_csc<T, Q, F><<<n, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, a.tiles + r.tile0, a.qtabs, a.pixels, a.status)
-    // the other output formats exist for the TMA variant only (B2J_USE_TMA=0 is a measurement knob of the BGRA path)
-    if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24); }
-    else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR); }
-    else if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA); }
-    else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false, B2J_OUT_BGRA); else B2J_IDCT_LAUNCH(false, true, B2J_OUT_BGRA); }
+    const uint32_t nc = r.tile_mid - r.tile0, ng = r.tile1 - r.tile_mid;
+#define B2J_IDCT_LAUNCH(T, Q, F, G) k_idct_csc<T, Q, F, G><<<(G) ? ng : nc, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, \
+        a.tiles + ((G) ? r.tile_mid : r.tile0), a.qtabs, a.pixels, a.status)
+    if (nc)
+    {
+        // the other output formats exist for the TMA variant only (B2J_USE_TMA=0 is a measurement knob of the BGRA path)
+        if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24, false); }
+        else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR, false); }
+        else if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA, false); }
+        else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false, B2J_OUT_BGRA, false); else B2J_IDCT_LAUNCH(false, true, B2J_OUT_BGRA, false); }
+    }
+    if (ng)
+    {
+        if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24, true); }
+        else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR, true); }
+        else { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA, true); }
+    }
 #undef B2J_IDCT_LAUNCH
 }
 

@@ -49,7 +49,8 @@ struct DecodeArgs
 };
 
 // A contiguous group of images of a batch: the unit the two-stream pipeline works on.
-struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1, scta0, scta1, simg0, simg1; };
+// Tiles of a part: [tile0, tile_mid) belong to three-component images, [tile_mid, tile1) to one-component images.
+struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1, scta0, scta1, simg0, simg1, tile_mid; };
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -151,6 +152,7 @@ int make_tensor_map(b2j_ctx *ctx, b2j_batch *b)
 
 uint32_t mode_of(const b2j_image_desc &d)
 {
+    if (d.tot_blks_per_mcu == 1) return kModeGray;
     switch (d.sampling[0])
     {
     case 0x11: return kMode444;
@@ -305,7 +307,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         ImgDev &im = b->imgs[(size_t)i];
         memset(&im, 0, sizeof(im));
         if (d.width <= 0 || d.height <= 0 || d.mcu_count <= 0 || d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset ||
-            d.scan_size >= 0x40000000ull || (d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
+            d.scan_size >= 0x40000000ull || (d.tot_blks_per_mcu != 1 && d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
         { rc = B2J_E_ARG; break; }
         img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
         img_scta0[(size_t)i] = (uint32_t)sctas.size(); img_simg0[(size_t)i] = (uint32_t)simgs.size();
@@ -407,7 +409,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             if (p == np - 1) i1 = n;
             b->parts.push_back({(uint32_t)i0, (uint32_t)i1, img_chunk0[(size_t)i0], img_chunk0[(size_t)i1], img_cta0[(size_t)i0], img_cta0[(size_t)i1],
                                 img_tile0[(size_t)i0], img_tile0[(size_t)i1], img_scta0[(size_t)i0], img_scta0[(size_t)i1],
-                                img_simg0[(size_t)i0], img_simg0[(size_t)i1]});
+                                img_simg0[(size_t)i0], img_simg0[(size_t)i1], 0u});
+            // the tiles of one-component images go behind the others: they have a kernel of their own
+            PartRange &pr = b->parts.back();
+            auto mid = std::stable_partition(tiles.begin() + pr.tile0, tiles.begin() + pr.tile1,
+                                             [](const TileDev &t) { return (t.info & 0xFFu) != kModeGray; });
+            pr.tile_mid = (uint32_t)(mid - tiles.begin());
             i0 = i1;
         }
         b->ev_huff.resize(b->parts.size());
@@ -542,7 +549,9 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b2j_batch_info &inf = b->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_images = n;
-    inf.kernel_launches = (int32_t)b->parts.size() * ((a.prepass_fused ? 1 : 3) + 1 + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
+    int idct_launches = 0;
+    for (const PartRange &pr : b->parts) idct_launches += (pr.tile_mid > pr.tile0 ? 1 : 0) + (pr.tile1 > pr.tile_mid ? 1 : 0);
+    inf.kernel_launches = idct_launches + (int32_t)b->parts.size() * ((a.prepass_fused ? 1 : 3) + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
     inf.scan_bytes = scan_bytes;

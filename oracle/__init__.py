@@ -23,6 +23,7 @@ ORC_E_UNSUPPORTED = -2
 ORC_E_DATA = -3
 GATE_REFERENCE = 0
 GATE_EXTENDED = 1
+GATE_GRAY = 4          # OR-able: one-component frames (extension beyond the reference, see oracle.c)
 
 
 def build(with_ref=True):

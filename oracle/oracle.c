@@ -31,6 +31,7 @@
 
 /* flags for orc_parse */
 #define ORC_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: only (22,11,11) and (11,11,11)   */
+#define ORC_GATE_GRAY 4      /* OR-able extension beyond the reference: one-component (grayscale) frames             */
 #define ORC_GATE_EXTENDED 1  /* also 4:2:2 (21,11,11) and 4:4:0 (12,11,11): the CPU loops of */
                              /* decoder.cpp:429-495 are generic for 1x1 chroma  */
 
@@ -135,10 +136,24 @@ static int orc_read_dqt(orc_image *img, orc_rd *r, size_t len)
 }
 
 /* parser.cpp:102-130 */
+/* Extension beyond the reference (gate flag ORC_GATE_GRAY): a one-component frame. The     */
+/* reference rejects it (parser.cpp:104-106 wants 3 components); the decode below is its loops with the two     */
+/* chroma components absent: one 8x8 block per MCU, U = V = 0 in YUV_to_RGB32 (decoder.cpp:367-370).            */
+static int g_allow_gray = 0;
 static int orc_read_sof(orc_image *img, orc_rd *r, size_t len)
 {
     uint8_t b[15];
     int i;
+    if (g_allow_gray && len == 9)
+    {
+        if (!rd_bytes(r, b, 9)) return 0;
+        if (b[5] != 1 || b[0] != 8 || b[7] != 0x11) return 0;
+        img->height = (b[1] << 8) | b[2];
+        img->width = (b[3] << 8) | b[4];
+        img->sampling[0] = 0x11; img->sampling[1] = img->sampling[2] = 0;
+        img->quant_id[0] = b[8]; img->quant_id[1] = img->quant_id[2] = b[8];
+        return 1;
+    }
     if (len != 15 || !rd_bytes(r, b, 15)) return 0;
     if (b[5] != 3 || b[0] != 8) return 0;
     img->height = (b[1] << 8) | b[2];
@@ -156,6 +171,13 @@ static int orc_read_sos(orc_image *img, orc_rd *r, size_t len)
 {
     uint8_t b[10];
     int i;
+    if (img->sampling[1] == 0 && img->sampling[2] == 0 && img->sampling[0] == 0x11)   /* one-component frame (extension) */
+    {
+        if (len != 6 || !rd_bytes(r, b, 6)) return 0;
+        if (b[0] != 1 || b[3] != 0 || b[4] != 0x3F || b[5] != 0) return 0;
+        img->huff_id[0] = img->huff_id[1] = img->huff_id[2] = b[2];
+        return 1;
+    }
     if (len != 10 || !rd_bytes(r, b, 10)) return 0;
     if (b[7] != 0 || b[8] != 0x3F || b[9] != 0) return 0;
     if (b[0] != 3) return 0;
@@ -232,6 +254,7 @@ static int orc_is_supported(const orc_image *img, int gate)
         if (!img->huff_present[dc]) return 0;
         if (!img->huff_present[ac | 0x10]) return 0;
     }
+    if (img->sampling[1] == 0 && img->sampling[2] == 0) return g_allow_gray && img->sampling[0] == 0x11;
     if (img->sampling[1] != 0x11 || img->sampling[2] != 0x11) return 0;
     if (img->sampling[0] == 0x22 || img->sampling[0] == 0x11) return 1;
     if (gate == ORC_GATE_EXTENDED && (img->sampling[0] == 0x21 || img->sampling[0] == 0x12)) return 1;
@@ -268,6 +291,8 @@ int orc_parse(const uint8_t *file, size_t len, int gate, orc_image *img)
     uint8_t tag[2], lb[2];
     r.p = file; r.len = len; r.pos = 0;
     memset(img, 0, sizeof(*img));
+    g_allow_gray = (gate & ORC_GATE_GRAY) != 0;
+    gate &= ~ORC_GATE_GRAY;
     if (!rd_bytes(&r, tag, 2) || tag[0] != 0xFF || tag[1] != 0xD8) return ORC_E_FORMAT;
     tag[1] = 0;
     while (rd_bytes(&r, tag, 2) && tag[1] >= 0xE0 && tag[1] <= 0xEF)
@@ -610,11 +635,12 @@ uint32_t orc_yuv_to_rgb32(int32_t Y, int32_t U, int32_t V)
 int orc_pixels(const orc_image *img, int32_t *mcu_data, uint8_t *bgra)
 {
     const int yh = img->sampling[0] >> 4, yv = img->sampling[0] & 0xF, yn = yh * yv;
-    const int ruh = yh / (img->sampling[1] >> 4), ruv = yv / (img->sampling[1] & 0xF);
-    const int rvh = yh / (img->sampling[2] >> 4), rvv = yv / (img->sampling[2] & 0xF);
+    const int gray = img->blks_per_mcu[1] == 0 && img->blks_per_mcu[2] == 0;
+    const int ruh = gray ? 1 : yh / (img->sampling[1] >> 4), ruv = gray ? 1 : yv / (img->sampling[1] & 0xF);
+    const int rvh = gray ? 1 : yh / (img->sampling[2] >> 4), rvv = gray ? 1 : yv / (img->sampling[2] & 0xF);
     int my, mx, blk, x, y;
     size_t out_blk = 0;
-    if (img->blks_per_mcu[1] != 1 || img->blks_per_mcu[2] != 1) return ORC_E_UNSUPPORTED;
+    if (!gray && (img->blks_per_mcu[1] != 1 || img->blks_per_mcu[2] != 1)) return ORC_E_UNSUPPORTED;
     for (my = 0; my < img->mcu_count_h; my++)
     {
         for (mx = 0; mx < img->mcu_count_w; mx++)
@@ -634,8 +660,8 @@ int orc_pixels(const orc_image *img, int32_t *mcu_data, uint8_t *bgra)
                     uint8_t *o;
                     if (px >= img->width) break;
                     Y = mat[((y >> 3) * yh + (x >> 3)) * 64 + (((y & 7) << 3) | (x & 7))];
-                    U = mat[yn * 64 + ((y / ruv) << 3) + x / ruh];
-                    V = mat[(yn + 1) * 64 + ((y / rvv) << 3) + x / rvh];
+                    U = gray ? 0 : mat[yn * 64 + ((y / ruv) << 3) + x / ruh];
+                    V = gray ? 0 : mat[(yn + 1) * 64 + ((y / rvv) << 3) + x / rvh];
                     rgb = orc_yuv_to_rgb32(Y, U, V);
                     o = bgra + ((size_t)py * img->width + px) * 4;
                     o[0] = (uint8_t)rgb; o[1] = (uint8_t)(rgb >> 8); o[2] = (uint8_t)(rgb >> 16); o[3] = (uint8_t)(rgb >> 24);

@@ -501,3 +501,57 @@ def test_randomised_batch_against_oracle(decoder, oracle):
             _check_pixels(pix[i], bgra)
     finally:
         oracle.set_strict(True)
+
+
+def _gray_jpeg(w, h, seed, quality, restart_mcus=0, optimize=False):
+    import io
+    from PIL import Image
+    px = synth.synth_pixels(w, h, seed)[:, :, 1]
+    buf = io.BytesIO()
+    kw = dict(format="JPEG", quality=quality, optimize=optimize)
+    if restart_mcus:
+        kw["restart_marker_blocks"] = int(restart_mcus)
+    Image.fromarray(px, "L").save(buf, **kw)
+    return buf.getvalue()
+
+
+def test_grayscale_extension(decoder, oracle):
+    """One-component frames (B2J_GATE_GRAY). The reference refuses them, so the check is
+    the oracle's extension -- the reference's own loops with the chroma components absent (U = V = 0) -- plus
+    Pillow as an independent decoder within the +-2 that separates the Chen-Wang IDCT from libjpeg's."""
+    import io
+    from PIL import Image
+    import ocljpegdecoder_b200 as b2j
+    from oracle import GATE_GRAY as ORC_GRAY, GATE_EXTENDED as ORC_EXT
+    specs = [(640, 480, 90, 16, False), (131, 77, 75, 0, False), (64, 64, 50, 1, True), (1, 1, 90, 0, False),
+             (333, 9, 95, 3, False), (1024, 768, 85, 0, True), (200, 120, 100, 0, False)]
+    files = [_gray_jpeg(w, h, 40 + i, q, ri, opt) for i, (w, h, q, ri, opt) in enumerate(specs)]
+    colour = synth.synth_jpeg(160, 96, 3, 90, "420", 4)
+    mix = files + [colour]
+    # refused without the flag, like the reference
+    rc, _ = b2j.parse_header(files[0], b2j.GATE_EXTENDED)
+    assert rc != 0
+    batch = decoder.batch(mix, gate=b2j.GATE_EXTENDED | b2j.GATE_GRAY)
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    oracle.set_strict(False)
+    try:
+        for i, f in enumerate(mix):
+            rc, img, coef, bgra = oracle.decode(f, gate=ORC_EXT | ORC_GRAY)
+            assert rc == 0, i
+            assert np.array_equal(batch.coefs(i), coef), i
+            got = batch.pixels(i)
+            _check_pixels(got, bgra)
+            if i < len(files):
+                assert np.array_equal(got[..., 0], got[..., 1]) and np.array_equal(got[..., 1], got[..., 2])
+                pil = np.asarray(Image.open(io.BytesIO(f)).convert("L"), dtype=np.int16)
+                assert np.abs(got[..., 0].astype(np.int16) - pil).max() <= 2, i
+    finally:
+        oracle.set_strict(True)
+    ref = [batch.pixels(i).copy() for i in range(len(mix))]
+    batch.set_output_format(b2j.OUT_RGB_PLANAR)
+    batch.decode()
+    for i, b in enumerate(ref):
+        assert np.array_equal(batch.pixels(i), np.moveaxis(b[..., 2::-1], 2, 0)), i
+    batch.close()
