@@ -107,3 +107,27 @@ def test_robust_parse_mode_accepts_what_the_reference_parser_chokes_on(built, or
     assert b2j.parse_header(fixture_jpeg, b2j.PARSE_ROBUST)[0] == 0
     # progressive stays rejected
     assert b2j.parse_header(base.replace(b"\xff\xc0", b"\xff\xc2", 1), b2j.PARSE_ROBUST)[0] != 0
+
+
+def test_grayscale_gate_flag(built, oracle):
+    """One-component frames are refused like the reference refuses them unless B2J_GATE_GRAY is set; with it the
+    geometry is one 8x8 block per MCU and agrees with the oracle's extension."""
+    import io
+    from PIL import Image
+    import ocljpegdecoder_b200 as b2j
+    from oracle import GATE_GRAY, GATE_EXTENDED
+    buf = io.BytesIO()
+    Image.fromarray(synth.synth_pixels(77, 45, 1)[:, :, 0], "L").save(buf, format="JPEG", quality=80)
+    f = buf.getvalue()
+    for gate in (b2j.GATE_REFERENCE, b2j.GATE_EXTENDED, b2j.GATE_EXTENDED | b2j.PARSE_ROBUST):
+        assert b2j.parse_header(f, gate)[0] != 0
+    rc, d = b2j.parse_header(f, b2j.GATE_EXTENDED | b2j.GATE_GRAY)
+    assert rc == 0
+    rco, o = oracle.parse(f, GATE_EXTENDED | GATE_GRAY)
+    assert rco == 0
+    assert (d.width, d.height, d.mcu_width, d.mcu_height, d.mcu_count, d.tot_blks_per_mcu, d.blk_count) == \
+           (o.width, o.height, o.mcu_width, o.mcu_height, o.mcu_count, o.tot_blks_per_mcu, o.blk_count) == (77, 45, 8, 8, 60, 1, 60)
+    assert d.scan_offset == o.scan_offset
+    # a colour file is unaffected by the flag
+    c = synth.synth_jpeg(64, 48, 2, 90, "420", 0)
+    assert b2j.parse_header(c, b2j.GATE_REFERENCE | b2j.GATE_GRAY)[0] == 0

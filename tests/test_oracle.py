@@ -127,3 +127,31 @@ def test_crafted_streams_oracle_vs_reference(oracle, reference):
                 qq = np.array(q[0] if b % tot < ny else q[1])
                 exp[b, zz] = blocks[b] * qq
             assert np.array_equal(coef, exp)
+
+
+def test_grayscale_extension_against_pillow(oracle):
+    """The oracle's one-component extension (GATE_GRAY; the reference refuses such files): the reference's loops
+    with the chroma components absent. Pillow (libjpeg) is the independent check: same coefficients after
+    dequantisation would be ideal, but libjpeg does not expose them -- pixels agree within +-2 (IDCT rounding)."""
+    import io
+    from PIL import Image
+    import synth
+    from oracle import GATE_GRAY, GATE_EXTENDED
+    oracle.set_strict(False)
+    try:
+        for i, (w, h, q, ri) in enumerate([(131, 77, 75, 0), (64, 64, 50, 1), (9, 200, 95, 3), (320, 240, 90, 16)]):
+            buf = io.BytesIO()
+            kw = dict(format="JPEG", quality=q)
+            if ri:
+                kw["restart_marker_blocks"] = ri
+            Image.fromarray(synth.synth_pixels(w, h, 60 + i)[:, :, 2], "L").save(buf, **kw)
+            f = buf.getvalue()
+            assert oracle.decode(f, gate=GATE_EXTENDED)[0] != 0
+            rc, img, coef, bgra = oracle.decode(f, gate=GATE_EXTENDED | GATE_GRAY)
+            assert rc == 0 and img.tot_blks_per_mcu == 1
+            assert coef.shape == (((w + 7) // 8) * ((h + 7) // 8), 64)
+            pil = np.asarray(Image.open(io.BytesIO(f)).convert("L"), dtype=np.int16)
+            assert np.abs(bgra[..., 0].astype(np.int16) - pil).max() <= 2
+            assert np.array_equal(bgra[..., 0], bgra[..., 1]) and np.array_equal(bgra[..., 1], bgra[..., 2]) and not bgra[..., 3].any()
+    finally:
+        oracle.set_strict(True)
