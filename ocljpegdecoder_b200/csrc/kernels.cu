@@ -588,7 +588,17 @@ k_unstuff_fused(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, co
             uint64_t w = probe;
             while (true)
             {
-                if (lane < j) { while ((w >> 62) == 0ull) w = st_load(probe_p); }
+                if (lane < j)
+                {
+                    // a predecessor publishes its aggregate a few microseconds after it starts; the bound only guards the
+                    // GPU against a hang should the in-order start of CTAs ever not hold (flagged, the image is then wrong)
+                    uint32_t spins = 0;
+                    while ((w >> 62) == 0ull)
+                    {
+                        if (++spins > (1u << 24)) { atomicOr(&status[img_idx], B2J_ST_INTERNAL); w = kStIncl; break; }
+                        w = st_load(probe_p);
+                    }
+                }
                 const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2ull);
                 const uint32_t upto = inc ? (uint32_t)__ffs(inc) - 1u : 31u;   // nearest inclusive word (lane order = distance)
                 uint32_t kk = lane <= upto ? (uint32_t)w : 0u;
