@@ -824,14 +824,20 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
     }
     if (ok_idx.empty()) return B2J_OK;
     const char *ge = getenv("B2J_HOST_GROUP");
-    size_t group = ge ? (size_t)atoi(ge) : 16;   // measured on B200: 16 images per group reaches the PCIe D2H floor
+    size_t group = ge ? (size_t)atoi(ge) : 32;   // measured on B200 (tests/e2e_probe.py): with the ramp below 32 .. 64 images per group are best
     if (group < 1) group = 1;
     struct Group { b2j_batch *b; size_t first, count; cudaEvent_t decoded; };
     std::vector<Group> groups;
     int rc = B2J_OK;
-    for (size_t g0 = 0; g0 < ok_idx.size() && rc == B2J_OK; g0 += group)
+    // The first groups are small (2, 4, 8, ... images): nothing travels device->host before the first group is
+    // parsed, staged, uploaded and decoded, so that lead time is kept short; later groups are `group` images.
+    const char *re = getenv("B2J_HOST_RAMP");
+    size_t ramp = (re && atoi(re) == 0) ? group : 2;
+    for (size_t g0 = 0, step = 0; g0 < ok_idx.size() && rc == B2J_OK; g0 += step)
     {
-        const size_t cnt = ok_idx.size() - g0 < group ? ok_idx.size() - g0 : group;
+        step = ramp < group ? ramp : group;
+        ramp *= 2;
+        const size_t cnt = ok_idx.size() - g0 < step ? ok_idx.size() - g0 : step;
         std::vector<b2j_image_desc> d(cnt);
         std::vector<const uint8_t *> f(cnt);
         std::vector<size_t> l(cnt);
