@@ -813,16 +813,9 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
     // Pipelined over groups of images: while group g's pixels travel device->host on the second stream,
     // group g+1 is parsed and staged on the host, uploaded and decoded on the first stream. The D2H copy
     // of the BGRA pixels is what bounds this call (PCIe), everything else hides behind it.
-    std::vector<b2j_image_desc> descs((size_t)n);
+    // Headers are parsed group by group, not all up front: the first pixels should be on their way early.
     std::vector<int> ok_idx;
     ok_idx.reserve((size_t)n);
-    for (int i = 0; i < n; i++)
-    {
-        const int rc = b2j_parse_header(files[i], lens[i], gate, &descs[(size_t)i]);
-        status[i] = rc;
-        if (rc == B2J_OK) ok_idx.push_back(i);
-    }
-    if (ok_idx.empty()) return B2J_OK;
     const char *ge = getenv("B2J_HOST_GROUP");
     size_t group = ge ? (size_t)atoi(ge) : 32;   // measured on B200 (tests/e2e_probe.py): with the ramp below 32 .. 64 images per group are best
     if (group < 1) group = 1;
@@ -833,19 +826,26 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
     // parsed, staged, uploaded and decoded, so that lead time is kept short; later groups are `group` images.
     const char *re = getenv("B2J_HOST_RAMP");
     size_t ramp = (re && atoi(re) == 0) ? group : 2;
-    for (size_t g0 = 0, step = 0; g0 < ok_idx.size() && rc == B2J_OK; g0 += step)
+    int next = 0;   // next file to parse
+    std::vector<b2j_image_desc> d;
+    std::vector<const uint8_t *> f;
+    std::vector<size_t> l;
+    while (next < n && rc == B2J_OK)
     {
-        step = ramp < group ? ramp : group;
+        const size_t step = ramp < group ? ramp : group;
         ramp *= 2;
-        const size_t cnt = ok_idx.size() - g0 < step ? ok_idx.size() - g0 : step;
-        std::vector<b2j_image_desc> d(cnt);
-        std::vector<const uint8_t *> f(cnt);
-        std::vector<size_t> l(cnt);
-        for (size_t k = 0; k < cnt; k++)
+        const size_t g0 = ok_idx.size();
+        d.clear(); f.clear(); l.clear();
+        while (next < n && d.size() < step)
         {
-            const int i = ok_idx[g0 + k];
-            d[k] = descs[(size_t)i]; f[k] = files[i]; l[k] = lens[i];
+            b2j_image_desc desc;
+            const int prc = b2j_parse_header(files[next], lens[next], gate, &desc);
+            status[next] = prc;
+            if (prc == B2J_OK) { ok_idx.push_back(next); d.push_back(desc); f.push_back(files[next]); l.push_back(lens[next]); }
+            next++;
         }
+        const size_t cnt = d.size();
+        if (cnt == 0) break;
         Group gr{nullptr, g0, cnt, nullptr};
         rc = b2j_batch_create(ctx, (int)cnt, d.data(), f.data(), l.data(), &gr.b);
         if (rc != B2J_OK) break;
@@ -865,6 +865,11 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
             e = cudaMemcpyAsync(dst, G.b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, ctx->stream2);
             if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyAsync D2H");
         }
+    }
+    for (; next < n; next++)   // only after a failure: every image still gets its header verdict
+    {
+        b2j_image_desc desc;
+        status[next] = b2j_parse_header(files[next], lens[next], gate, &desc);
     }
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream2);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
