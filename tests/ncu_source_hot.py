@@ -8,7 +8,13 @@ data = [r for r in rows[2:] if len(r) >= len(hdr) - 2]
 ia, isamp, iexe = hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
 stall = {h: i for i, h in enumerate(hdr) if h.startswith('stall_') and '(' not in h}
 ex = []
+seen = set()
+iaddr = hdr.index('Address') if 'Address' in hdr else None
 for k, r in enumerate(data):
+    if iaddr is not None:
+        if r[iaddr] in seen:   # the CSV lists a kernel's SASS once per view
+            continue
+        seen.add(r[iaddr])
     try:
         e = int(r[iexe]); s = int(r[isamp])
     except ValueError:
