@@ -232,7 +232,9 @@ extern "C" int b2j_parse_header(const uint8_t *file, size_t len, int gate_flags,
             derive_geometry(d);
             d.scan_offset = r.pos;
             d.scan_size = len - r.pos;
-            return B2J_OK;
+            // a file that ends right behind the SOS header has no entropy-coded data at all: the reference gives up
+            // on it with "data incomplete" (decoder.cpp:310-314)
+            return d.scan_size ? B2J_OK : B2J_E_DATA;
         }
         default:   // SOF1..3 (parser.cpp:347-352), EOI, COM, late APPn: the reference stops here
             return tag[1] >= 0xC1 && tag[1] <= 0xC3 ? B2J_E_UNSUPPORTED : B2J_E_FORMAT;

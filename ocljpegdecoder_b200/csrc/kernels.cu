@@ -991,6 +991,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + kZzBytes + tid * kRingBytesPerLane);
     else reinterpret_cast<BitReader<1> &>(br).init(base, decodable ? start : 0u);
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
+    const uint32_t seg_bytes = end > start ? end - start : 0u;   // !SYNC: what the lane may consume
     if (SYNC) br.bitpos += start_bit & 7u;
     bool dead = !decodable;
 
@@ -1077,6 +1078,14 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         }
         __syncwarp();
         if (WIDE) reinterpret_cast<RingReader &>(br).round_boundary();
+        // A lane whose segment is truncated or corrupt must not keep reading whatever follows it (other images,
+        // the scratch arrays, the end of the allocation): once it has fetched more than its segment holds, plus the
+        // reader's look-ahead, it stops and the image is flagged (decoder.cpp:310-314 "data incomplete").
+        if (!SYNC && !dead)
+        {
+            const uint32_t nw_now = WIDE ? br.words_consumed() : reinterpret_cast<BitReader<1> &>(br).words_fetched();
+            if (nw_now * 4u > seg_bytes + 16u) { err |= B2J_ST_OVERRUN; dead = true; }
+        }
         bi = (bi + 1 == tot) ? 0u : bi + 1;
     }
 
@@ -1968,7 +1977,7 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
         uint32_t spins = 0;
         while (!mbar_try_wait(&sm.bar[0], 0))
         {
-            if (++spins > (1u << 22)) { if (tid == 0) atomicOr(&status[d.img], 0x4000); break; }   // never hang the GPU
+            if (++spins > (1u << 22)) { if (tid == 0) atomicOr(&status[d.img], B2J_ST_INTERNAL); break; }   // never hang the GPU
         }
     }
     else

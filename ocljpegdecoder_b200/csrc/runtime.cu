@@ -124,6 +124,7 @@ struct b2j_batch
     std::vector<PartRange> parts;
     std::vector<cudaEvent_t> ev_huff, ev_idct;   // per part: entropy decode done / pixels done
     bool uploaded;
+    cudaStream_t last_stream;   // the stream the batch was last uploaded / decoded / read on
 };
 
 namespace {
@@ -162,7 +163,38 @@ uint32_t mode_of(const b2j_image_desc &d)
     }
 }
 
-cudaStream_t pick_stream(const b2j_batch *b, void *stream) { return stream ? (cudaStream_t)stream : b->ctx->stream; }
+// The descriptor is caller-supplied: every derived field is recomputed from width, height and the sampling
+// factors (decoder.cpp:161-192) and must agree, so that no kernel ever indexes with an inconsistent geometry.
+bool geometry_ok(const b2j_image_desc &d)
+{
+    if (d.width <= 0 || d.height <= 0 || d.width > 65535 || d.height > 65535) return false;
+    const bool gray = d.color_space == B2J_CS_GRAY;
+    int mh = 0, mv = 0, tot = 0, blks[3] = {0, 0, 0};
+    for (int c = 0; c < (gray ? 1 : 3); c++)
+    {
+        const int h = d.sampling[c] >> 4, v = d.sampling[c] & 0xF;
+        if (h < 1 || h > 4 || v < 1 || v > 4) return false;
+        mh = h > mh ? h : mh; mv = v > mv ? v : mv;
+        blks[c] = h * v; tot += h * v;
+    }
+    if (tot > 10) return false;
+    const int mcw = (d.width - 1) / (8 * mh) + 1, mch = (d.height - 1) / (8 * mv) + 1;
+    if (d.mcu_width != 8 * mh || d.mcu_height != 8 * mv || d.mcu_count_w != mcw || d.mcu_count_h != mch) return false;
+    if (d.mcu_count != mcw * mch || d.tot_blks_per_mcu != tot || d.blk_count != d.mcu_count * tot) return false;
+    for (int c = 0; c < 3; c++)
+        if (d.blks_per_mcu[c] != blks[c] || d.quant_id[c] > 3) return false;
+    if (d.restart_interval < 0) return false;
+    return true;
+}
+
+cudaStream_t pick_stream(b2j_batch *b, void *stream) { return b->last_stream = (stream ? (cudaStream_t)stream : b->ctx->stream); }
+
+void destroy_events(b2j_batch *b)
+{
+    for (auto &e : b->ev_huff) if (e) cudaEventDestroy(e);
+    for (auto &e : b->ev_idct) if (e) cudaEventDestroy(e);
+    b->ev_huff.clear(); b->ev_idct.clear();
+}
 
 void release_batch_buffers(b2j_batch *b)
 {
@@ -233,24 +265,41 @@ extern "C" int b2j_create(int device, b2j_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->encode_tiled = nullptr;
-    CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    ctx->stream = ctx->stream2 = nullptr;
     {
         const char *pe = getenv("B2J_PARTS");
         ctx->n_parts = pe ? atoi(pe) : 1;   // > 1 was measured slower on B200: the entropy decoder is one wave
         if (ctx->n_parts < 1) ctx->n_parts = 1;
         if (ctx->n_parts > 16) ctx->n_parts = 16;
     }
-    CU_TRY(init_constants());
-    CU_TRY(configure_kernels(kLutMaxEntries));
+    cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = init_constants();
+    if (ce == cudaSuccess) ce = configure_kernels(kLutMaxEntries);
+    if (ce != cudaSuccess)
+    {
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+        delete ctx;
+        return fail_cuda(ce, "b2j_create");
+    }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
         ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     else
         cudaGetLastError();
+    if (!ctx->encode_tiled)
+    {
+        // every colour kernel but the BGRA measurement variant loads its tile through a tensor map
+        cudaStreamDestroy(ctx->stream);
+        cudaStreamDestroy(ctx->stream2);
+        delete ctx;
+        t_last_error = "the driver does not export cuTensorMapEncodeTiled (needed for the TMA tile loads)";
+        return B2J_E_CUDA;
+    }
     const char *env = getenv("B2J_USE_TMA");
-    ctx->use_tma = ctx->encode_tiled != nullptr && !(env && env[0] == '0');
+    ctx->use_tma = !(env && env[0] == '0');
     *out = ctx;
     return B2J_OK;
 }
@@ -283,6 +332,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->d_coef = nullptr; b->d_expand = nullptr;
     b->h_blob_cap = b->d_blob_cap = b->d_scratch_cap = b->d_coef_cap = b->d_pix_cap = b->d_expand_cap = 0;
     b->uploaded = false;
+    b->last_stream = nullptr;
 
     std::vector<uint32_t> chunk_img;
     std::vector<uint32_t> img_cta0((size_t)n + 1), img_tile0((size_t)n + 1), img_chunk0((size_t)n + 1);
@@ -306,9 +356,10 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         const b2j_image_desc &d = descs[i];
         ImgDev &im = b->imgs[(size_t)i];
         memset(&im, 0, sizeof(im));
-        if (d.width <= 0 || d.height <= 0 || d.mcu_count <= 0 || d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset ||
-            d.scan_size >= 0x40000000ull || (d.tot_blks_per_mcu != 1 && d.tot_blks_per_mcu != 3 && d.tot_blks_per_mcu != 4 && d.tot_blks_per_mcu != 6))
-        { rc = B2J_E_ARG; break; }
+        // bit positions are 32-bit on the device (scan_size * 8 must fit); an empty scan (file cut right behind the SOS
+        // header) has nothing to decode -- the reference fails it with "data incomplete" (decoder.cpp:310-314)
+        if (d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset || d.scan_size == 0 || d.scan_size >= 0x1FFFFFFFull || !geometry_ok(d))
+        { rc = d.scan_size == 0 && d.scan_offset <= lens[i] ? B2J_E_DATA : B2J_E_ARG; break; }
         img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
         img_scta0[(size_t)i] = (uint32_t)sctas.size(); img_simg0[(size_t)i] = (uint32_t)simgs.size();
         im.raw_off = raw_total;
@@ -419,10 +470,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         }
         b->ev_huff.resize(b->parts.size());
         b->ev_idct.resize(b->parts.size());
+        for (size_t p = 0; p < b->parts.size(); p++) b->ev_huff[p] = b->ev_idct[p] = nullptr;
         for (size_t p = 0; p < b->parts.size(); p++)
         {
-            CU_TRY(cudaEventCreateWithFlags(&b->ev_huff[p], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&b->ev_idct[p], cudaEventDisableTiming));
+            cudaError_t e = cudaEventCreateWithFlags(&b->ev_huff[p], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_idct[p], cudaEventDisableTiming);
+            if (e != cudaSuccess) { destroy_events(b); delete b; return fail_cuda(e, "cudaEventCreateWithFlags"); }
         }
     }
 
@@ -476,7 +529,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             cudaGetLastError();
         }
     }
-    if (rc != B2J_OK) { release_batch_buffers(b); delete b; return rc == B2J_E_CUDA ? B2J_E_NOMEM : rc; }
+    if (rc != B2J_OK) { destroy_events(b); release_batch_buffers(b); delete b; return rc == B2J_E_CUDA ? B2J_E_NOMEM : rc; }
 
     // ---- fill the pinned blob
     memcpy(b->h_blob + b->off_imgs, b->imgs.data(), sizeof(ImgDev) * (size_t)n);
@@ -498,7 +551,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     }
 
     rc = make_tensor_map(ctx, b);
-    if (rc != B2J_OK) { release_batch_buffers(b); delete b; return rc; }
+    if (rc != B2J_OK) { destroy_events(b); release_batch_buffers(b); delete b; return rc; }
 
     DecodeArgs &a = b->args;
     a.raw = b->d_blob + b->off_raw;
@@ -568,10 +621,11 @@ extern "C" void b2j_batch_destroy(b2j_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
+    // the buffers go back to the pool: nothing enqueued on them may still be in flight, including work on a caller's stream
+    if (b->last_stream && b->last_stream != b->ctx->stream && b->last_stream != b->ctx->stream2) cudaStreamSynchronize(b->last_stream);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStreamSynchronize(b->ctx->stream2);
-    for (auto &e : b->ev_huff) cudaEventDestroy(e);
-    for (auto &e : b->ev_idct) cudaEventDestroy(e);
+    destroy_events(b);
     release_batch_buffers(b);
     delete b;
 }
@@ -682,9 +736,13 @@ extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t s = pick_stream(b, stream);
     const size_t per = events_per_step(b);
-    std::vector<cudaEvent_t> ev((size_t)steps * per);
-    for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
+    std::vector<cudaEvent_t> ev((size_t)steps * per, nullptr);
     int rc = B2J_OK;
+    for (auto &e : ev)
+    {
+        const cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) { rc = fail_cuda(ce, "cudaEventCreate"); e = nullptr; break; }
+    }
     for (int k = 0; k < steps && rc == B2J_OK; k++) rc = enqueue_decode(b, s, &ev[(size_t)k * per]);
     if (rc == B2J_OK)
     {
@@ -696,7 +754,7 @@ extern "C" int b2j_batch_decode_steps(b2j_batch *b, void *stream, int steps, b2j
         for (int k = 0; k < steps && per_step; k++) collect_times(b, &ev[(size_t)k * per], &per_step[k]);
         if (total_ms) cudaEventElapsedTime(total_ms, ev[0], ev[(size_t)(steps - 1) * per + 1]);
     }
-    for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
     return rc;
 }
 
