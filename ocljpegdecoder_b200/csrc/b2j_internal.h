@@ -17,13 +17,21 @@ constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of r
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
 constexpr int kSubBytes = 128;           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
 constexpr int kSyncRounds = 6;           // parallel synchronisation rounds before the sequential sweep
+constexpr int kSyncPre = 2;              // chunk-wise synchronisation (b2j_sync.h): sub-sequences walked in front of a chunk
+constexpr int kSyncLanes = kHuffThreads - kSyncPre;   // output sub-sequences per chunk
 #ifndef B2J_LUT_BITS
 #define B2J_LUT_BITS 10
 #endif
 constexpr int kLutBits = B2J_LUT_BITS;   // primary Huffman LUT width, AC tables (one lookup per coefficient)
 constexpr int kLutBitsDc = 6;            // DC tables (one lookup per block): small, the shared memory goes to the stream rings
-constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set
-constexpr int kLutMaxEntries = 12288;    // u16 entries of one LUT set (24 KB of shared memory)
+constexpr int kLutHeader = 16;           // u16 words of header in front of a LUT set:
+                                         //   [0..2] DC table of component c, [3..5] AC table (decode tables, entry format below)
+                                         //   [6..8] DC walk table, [9..11] AC walk table (self-synchronisation walks, b2j_sync.h)
+                                         //   [12]   length of the decode part of the set (header + decode tables), a multiple of 8
+constexpr int kLutMaxDecode = 12288;     // u16 entries of the decode part of a LUT set (24 KB of shared memory)
+constexpr int kLutMaxEntries = 32768;    // u16 entries of a whole LUT set, walk tables included (64 KB)
+constexpr int kWalkBitsAc = 12;          // index width of the AC walk tables (several symbols per lookup)
+constexpr int kWalkBitsDc = 9;           // index width of the DC walk tables
 constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
 constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
@@ -38,6 +46,14 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //   escape  : bits 0-5  = extra index bits nb (1..16 - primary width, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
 //             offset relative to the end of the primary table, in units of kLutSubAlign entries
 //   invalid : 0 (no codeword has this prefix)
+// Walk table entry (u16), used by the walks of the self-synchronising path only (they need no coefficient values):
+//   AC : the symbols whose CODES lie completely inside the next kWalkBitsAc bits, up to and including an end-of-block:
+//        bits 0-4 = bits consumed by all of them (codes + value bits, <= 31), bits 9-14 = scan positions they need
+//        (sum of run + 1, plus 1 when the last of them is the end-of-block symbol: the block must not be complete
+//        in front of it; <= 63), bit 15 = the last one is the end-of-block symbol. A step is valid where
+//        position + bits 9-14 <= 64 (a block that fills up without an end-of-block code ends a group early)
+//   DC : one symbol: bits 0-4 = code length + category, bits 9-13 = category (0..16)
+//   0  : take the one-symbol path through the decode tables (code longer than the index, no codeword, category > 16)
 constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table
 
@@ -62,7 +78,8 @@ struct ImgDev
     uint32_t has_dri;
     uint32_t width, height;
     uint32_t lut_off;      // u16 offset of the LUT set in luts[]
-    uint32_t lut_len;      // u16 length of the LUT set (header included)
+    uint32_t lut_len;      // u16 length of the LUT set (header, decode tables, walk tables)
+    uint32_t lut_dec_len;  // u16 length of its decode part (what k_huff_decode stages)
     uint32_t mode;         // SamplingMode
     uint32_t tot_blks;     // blocks per MCU
     uint32_t ny_blks;      // luma blocks per MCU
@@ -106,6 +123,9 @@ struct TileDev
 // Canonical Huffman table -> two-level LUT. Returns false when the table cannot be built
 // (code space overflow) or needs more than `max_entries` entries.
 bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out, size_t max_entries);
+
+// Canonical Huffman table -> walk table (1 << kWalkBitsDc or 1 << kWalkBitsAc entries, format above).
+bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out);
 
 // LUT set for one image: header (offsets of the DC/AC table of each component) + tables.
 bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out);

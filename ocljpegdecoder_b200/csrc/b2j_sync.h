@@ -1,0 +1,366 @@
+// b2j_sync.h -- the self-synchronisation of one "chunk" of a stream without restart markers, written once for
+// the device (kernels.cu: k_sync_chunks / k_sync_sweep, one CTA per chunk, one thread per lane, phases separated by
+// __syncthreads) and for a host emulation (tests/native/synccheck.cpp: the same phases run lane after lane), so that
+// the round / merge / bookkeeping logic can be checked on a machine without a GPU.
+//
+// Replaces the serial scan loop of decode_huffman_data() (reference decoder.cpp:286-346) by a parallel search for
+// the decoder state at every sub-sequence border.
+//
+// A chunk is kSyncLanes consecutive sub-sequences (kSubBytes * 8 bits each) of one image's clean stream plus up to
+// kSyncPre sub-sequences in front of them (the "pre-lanes"), which are walked only to give the first lane of the
+// chunk a state that is in step with the true decoder.
+//   round 0   every lane walks its own sub-sequence from a guessed state (its border, block 0, DC expected), in two
+//             halves; the state at the first symbol at or behind the middle plus what the second half contributes
+//             are kept as a checkpoint;
+//   round r   a lane whose predecessor's exit state is not the entry state it last started from walks again from
+//             that exit state, up to the middle: a decoder that started from a wrong state falls into step with the
+//             true one within a few dozen symbols, so nearly always it arrives exactly at the checkpoint -- then
+//             round 0's second half stands and the exit state does not change; otherwise it walks on to the end.
+//             Rounds repeat until no lane's entry state changes any more: lane k of the chunk is final after at most
+//             k rounds, in practice after two or three. Everything lives in shared memory; no global round trips,
+//             no launches between rounds.
+//   output    per lane the record the decode kernel needs (blocks started, DC sums, first block start), per chunk
+//             the entry state it assumed, its exit state and its totals.
+// A chunk's result is right if the entry state of its first lane is right. For the first chunk of an image that is
+// the true start state; for every other chunk it is the exit state of its pre-lanes, i.e. right unless the guess
+// failed to fall into step within kSyncPre sub-sequences. k_sync_sweep compares every chunk's assumed entry with its
+// predecessor's exit and re-runs the (rare) chunks that disagree, in order, with the entry forced: correctness never
+// depends on luck.
+#ifndef B2J_SYNC_H_INCLUDED
+#define B2J_SYNC_H_INCLUDED
+
+#include <stdint.h>
+
+#include "b2j_internal.h"
+
+#ifdef __CUDACC__
+#define B2J_HD __host__ __device__ __forceinline__
+#else
+#define B2J_HD inline
+#endif
+
+#ifndef __CUDACC__
+// host emulation (tests/native/synccheck.cpp): the two CUDA vector types this header uses
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 v = {x, y}; return v; }
+#endif
+
+// host emulation only: counts walk-table steps [0] and one-symbol steps [1]
+#if defined(B2J_WALK_STATS) && !defined(__CUDACC__)
+extern uint64_t g_b2j_walk_steps[2];
+#define B2J_WALK_COUNT(k) (g_b2j_walk_steps[k]++)
+#else
+#define B2J_WALK_COUNT(k) ((void)0)
+#endif
+
+namespace b2j {
+
+// ---- arithmetic shared by device and host ---------------------------------------------------------------------
+// high word of (hi:lo) << (sh & 31)
+B2J_HD uint32_t fsh_l(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
+#endif
+}
+B2J_HD uint32_t bswap32(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
+// Value bits -> signed coefficient (JPEG EXTEND, decoder.cpp:72-82). v: the bits left-aligned, size = their number
+// (0 -> 0). A leading 1 bit means positive.
+B2J_HD int32_t extend_bits(uint32_t v, uint32_t size)
+{
+    const uint32_t u = fsh_l(v, 0u, size);                   // the value bits as a number: v >> (32 - size)
+    const uint32_t neg = (uint32_t)((int32_t)~v >> 31);      // all ones when the leading bit is 0
+    return (int32_t)(u - fsh_l(neg, 0u, size));              // negative: u - (2^size - 1)
+}
+
+// The image's clean stream as 32-bit words in global memory (device) / host memory.
+struct StreamWords
+{
+    const uint32_t *w;
+    B2J_HD uint32_t get(uint32_t i) const
+    {
+#ifdef __CUDA_ARCH__
+        return __ldg(w + i);
+#else
+        return w[i];
+#endif
+    }
+};
+
+// MSB-first bit reader: a 64-bit window (cur:nxt) and one raw word of look-ahead (requested one refill early).
+// Same scheme as BitStream's cached reader (bitstream.h:311-365), 32 bits at a time.
+struct WalkReader
+{
+    uint32_t cur, nxt, raw, bitpos, wi;
+    StreamWords src;
+    B2J_HD void init(const StreamWords &s, uint32_t byte_off)
+    {
+        src = s;
+        wi = byte_off >> 2;
+        cur = bswap32(src.get(wi));
+        nxt = bswap32(src.get(wi + 1u));
+        raw = src.get(wi + 2u);
+        wi += 3u;
+        bitpos = (byte_off & 3u) * 8u;
+    }
+    B2J_HD uint32_t peek() const { return fsh_l(nxt, cur, bitpos); }
+    B2J_HD void skip(uint32_t n)   // n <= 32
+    {
+        bitpos += n;
+        if (bitpos >= 32u)
+        {
+            cur = nxt;
+            nxt = bswap32(raw);
+            raw = src.get(wi);
+            wi++;
+            bitpos -= 32u;
+        }
+    }
+};
+
+struct WalkState { uint32_t p, c, z; };
+
+struct WalkResult
+{
+    uint32_t p, cz, nblk, fs, fc;
+    int32_t dc0, dc1, dc2;
+};
+
+// Decode tables of one image as the walk sees them. LUT: at(i) reads entry i of the set (u16 units from its start;
+// shared memory on the device), hdr(i) the i-th header word.
+struct WalkTabs
+{
+    uint32_t walk[3];     // per component: DC walk table | AC walk table << 16 (u16 offsets in the set)
+    uint32_t dec[3];      // per component: DC decode table | AC decode table << 16
+};
+
+template <class LUT>
+B2J_HD WalkTabs walk_tabs(const LUT &lut)
+{
+    WalkTabs t;
+    for (int c = 0; c < 3; c++)
+    {
+        t.walk[c] = lut.hdr(6 + c) | lut.hdr(9 + c) << 16;
+        t.dec[c] = lut.hdr(c) | lut.hdr(3 + c) << 16;
+    }
+    return t;
+}
+
+// One symbol through the two-level decode tables (entry format: b2j_internal.h). Returns the leaf, 0 = no codeword.
+template <class LUT>
+B2J_HD uint32_t lookup_symbol(const LUT &lut, uint32_t tab, uint32_t pk, uint32_t bits)
+{
+    uint32_t e = lut.at(tab + (pk >> (32u - bits)));
+    if (!(e & 32u) && e != 0u)
+    {
+        const uint32_t nb = e & 63u, off = (e >> 6) * kLutSubAlign;
+        e = lut.at(tab + (1u << bits) + off + ((pk << bits) >> (32u - nb)));
+    }
+    return (e & 32u) ? e : 0u;
+}
+
+// Walks the stream from state `s` while the next symbol starts before bit `limit`. No output but the result:
+// exit state, blocks started (DC symbols met), their DC sums per component and the first block start.
+// On a valid stream, from a true state, the walk follows the reference's decoder (decoder.cpp:221-260 inside the
+// loops of decoder.cpp:286-346) and ends in its state at the first symbol boundary at or behind `limit`, however the
+// symbols were grouped on the way: an AC walk-table step covers several symbols at once, and is taken only while the
+// walk is more than kWalkBitsAc - 1 bits in front of `limit` (every symbol of a group starts inside the index window)
+// and the block cannot fill up in front of the group's last symbol; otherwise, and wherever the walk table has no
+// entry, one symbol is taken through the decode tables.
+// From any state -- true or guessed -- the result is a function of that state alone, which is all the
+// synchronisation needs (a guessed walk that reaches a state of the true walk continues exactly like it).
+// nu: blocks of component 1 per MCU (component = (c >= ny) + (c >= ny + nu)).
+template <class LUT>
+B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const WalkTabs &tabs, WalkState s, uint32_t limit,
+                              uint32_t tot, uint32_t ny, uint32_t nu)
+{
+    WalkResult r;
+    r.nblk = 0; r.fs = kSubNone; r.fc = 0; r.dc0 = r.dc1 = r.dc2 = 0;
+    uint32_t p = s.p, c = s.c, z = s.z;
+    bool bad = false;
+    if (p < limit)
+    {
+        WalkReader br;
+        br.init(stream, p >> 3);
+        br.bitpos += p & 7u;
+        const uint32_t lim_group = limit > (uint32_t)kWalkBitsAc ? limit - (uint32_t)(kWalkBitsAc - 1) : 0u;
+        const uint32_t nyu = ny + nu;
+        uint32_t comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
+        uint32_t tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
+        uint32_t tdc = tw & 0xFFFFu, tac = tw >> 16;
+        while (p < limit)
+        {
+            const uint32_t pk = br.peek();
+            const bool dc = z == 0u;
+            // one lookup for either kind of symbol
+            const uint32_t e = lut.at((dc ? tdc : tac) + (pk >> (dc ? 32u - (uint32_t)kWalkBitsDc : 32u - (uint32_t)kWalkBitsAc)));
+            uint32_t nb, f;
+            // a group is taken whole only in front of the limit and where the block cannot fill up inside it
+            if (e != 0u && p < lim_group && z + ((e >> 9) & 63u) <= 64u)
+            {
+                nb = e & 31u;     // bits this step consumes
+                f = e >> 9;       // AC: scan positions advanced (+ 64 when the group ends the block); DC: category
+                B2J_WALK_COUNT(0);
+            }
+            else
+            {
+                B2J_WALK_COUNT(1);
+                const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
+                const uint32_t e1 = dc ? lookup_symbol(lut, td & 0xFFFFu, pk, (uint32_t)kLutBitsDc) : lookup_symbol(lut, td >> 16, pk, (uint32_t)kLutBits);
+                if (e1 == 0u) { bad = true; break; }
+                const uint32_t size = (e1 >> 6) & (dc ? 31u : 15u);
+                nb = (e1 & 31u) + size;
+                f = dc ? size : (e1 >> 10) + 1u;   // AC: zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
+            }
+            uint32_t zn = z + f;
+            if (dc)
+            {
+                // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
+                const int32_t diff = extend_bits(pk << (nb - f), f);
+#ifdef B2J_WALK_DEBUG
+                fprintf(stderr, "  walk dc p %u nb %u f %u e %x diff %d comp %u\n", p, nb, f, e, diff, comp);
+#endif
+                if (r.nblk == 0u) { r.fs = p; r.fc = c; }
+                r.nblk++;
+                r.dc0 += comp == 0u ? diff : 0;
+                r.dc1 += comp == 1u ? diff : 0;
+                r.dc2 += comp == 2u ? diff : 0;
+                zn = 1u;
+            }
+            z = zn;
+            p += nb;
+            br.skip(nb);
+            if (z >= 64u)
+            {
+                // the block is complete: next block of the MCU
+                z = 0u;
+                c = (c + 1u == tot) ? 0u : c + 1u;
+                comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
+                tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
+                tdc = tw & 0xFFFFu; tac = tw >> 16;
+            }
+        }
+    }
+    // A non-code can only be met by a walk that started from a wrong guess (or in a corrupt stream, which the final
+    // decode flags): hand the next lane the same guess a first-round walk would use instead of a dead state, so
+    // that a wrong guess never poisons the records downstream.
+    r.p = bad ? (p > limit ? p : limit) : p;
+    r.cz = bad ? 0u : (c | (z << 8));
+    return r;
+}
+
+// Per-lane scratch of a chunk (shared memory on the device). Index = lane = thread.
+struct SyncShared
+{
+    SubRec cur[kHuffThreads];       // the lane's record as of the latest round (exit state, totals, first block start)
+    SubMid mid[kHuffThreads];       // round 0: state at the middle + the second half's contribution
+    uint2 r0_exit[kHuffThreads];    // round 0: exit state (p, cz) -- stands whenever a later walk meets the checkpoint
+    uint2 entry_used[kHuffThreads]; // the entry state (p, cz) cur[] was computed from
+    uint2 entry_next[kHuffThreads]; // round r: the entry state to start from (the predecessor's exit state before the round)
+};
+
+// What a chunk is, for every lane alike.
+struct SyncChunk
+{
+    uint32_t first;        // first OUTPUT sub-sequence of the chunk (lane kSyncPre)
+    uint32_t n_sub;        // sub-sequences of the image
+    uint32_t bits;         // length of the image's clean stream in bits
+    uint32_t tot, ny;      // blocks per MCU, luma blocks per MCU
+    uint32_t first_lane;   // first active lane: kSyncPre unless pre-lanes are in use (then max(0, kSyncPre - first))
+    bool forced;           // the entry state of lane first_lane is given (true start of the image, or the sweep)
+    uint2 forced_entry;    // (p, cz)
+};
+
+B2J_HD bool sync_lane_active(const SyncChunk &ch, uint32_t t)
+{
+    return t >= ch.first_lane && ch.first + t - (uint32_t)kSyncPre < ch.n_sub;
+}
+B2J_HD uint32_t sync_lane_sub(const SyncChunk &ch, uint32_t t) { return ch.first + t - (uint32_t)kSyncPre; }
+
+B2J_HD void sync_set(SubRec &d, const WalkResult &r)
+{
+    d.p = r.p; d.cz = r.cz; d.nblk = r.nblk; d.dc[0] = r.dc0; d.dc[1] = r.dc1; d.dc[2] = r.dc2; d.fs = r.fs; d.fc = r.fc;
+}
+
+// Walk of sub-sequence `s` from `entry`: first half, checkpoint test (when `check`), second half.
+// Returns true when the walk met the round-0 checkpoint of the lane (then round 0's second half stands).
+template <class W>
+B2J_HD bool sync_walk_lane(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, uint2 entry, bool round0)
+{
+    const uint32_t s = sync_lane_sub(ch, t);
+    const uint32_t lo = s * (uint32_t)(kSubBytes * 8);
+    const uint32_t hi = lo + (uint32_t)(kSubBytes * 8) < ch.bits ? lo + (uint32_t)(kSubBytes * 8) : ch.bits;
+    const uint32_t md = lo + (uint32_t)(kSubBytes * 4) < hi ? lo + (uint32_t)(kSubBytes * 4) : hi;
+    const WalkState s0 = {entry.x, entry.y & 0xFFu, entry.y >> 8};
+    const WalkResult ra = w.walk(s0, md);
+    if (!round0)
+    {
+        const SubMid &m = sh.mid[t];
+        if (ra.p == m.p && ra.cz == m.cz)
+        {
+            // in step at the middle: first half of this walk + second half of round 0; the exit state of round 0 stands
+            SubRec &c = sh.cur[t];
+            c.p = sh.r0_exit[t].x; c.cz = sh.r0_exit[t].y;
+            c.nblk = ra.nblk + m.nblk;
+            c.dc[0] = ra.dc0 + m.dc[0]; c.dc[1] = ra.dc1 + m.dc[1]; c.dc[2] = ra.dc2 + m.dc[2];
+            c.fs = ra.fs != kSubNone ? ra.fs : m.fs;
+            c.fc = ra.fs != kSubNone ? ra.fc : m.fc;
+            sh.entry_used[t] = entry;
+            return true;
+        }
+    }
+    const WalkState s1 = {ra.p, ra.cz & 0xFFu, ra.cz >> 8};
+    const WalkResult rb = w.walk(s1, hi);
+    WalkResult r = rb;   // exit state of the second half
+    r.nblk = ra.nblk + rb.nblk; r.dc0 = ra.dc0 + rb.dc0; r.dc1 = ra.dc1 + rb.dc1; r.dc2 = ra.dc2 + rb.dc2;
+    if (ra.fs != kSubNone) { r.fs = ra.fs; r.fc = ra.fc; }
+    sync_set(sh.cur[t], r);
+    sh.entry_used[t] = entry;
+    if (round0)
+    {
+        SubMid &m = sh.mid[t];
+        m.p = ra.p; m.cz = ra.cz; m.nblk = rb.nblk; m.dc[0] = rb.dc0; m.dc[1] = rb.dc1; m.dc[2] = rb.dc2; m.fs = rb.fs; m.fc = rb.fc;
+        sh.r0_exit[t] = make_uint2(rb.p, rb.cz);
+    }
+    return false;
+}
+
+// Phase "round 0" of lane t.
+template <class W>
+B2J_HD void sync_phase_round0(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t)
+{
+    if (!sync_lane_active(ch, t)) return;
+    const uint32_t s = sync_lane_sub(ch, t);
+    const bool given = ch.forced && t == ch.first_lane;
+    const uint2 entry = given ? ch.forced_entry : make_uint2(s * (uint32_t)(kSubBytes * 8), 0u);
+    sync_walk_lane(w, ch, sh, t, entry, true);
+}
+
+// Phase "need" of lane t: does the lane have to walk again? (reads the predecessor's exit state BEFORE the round)
+B2J_HD bool sync_phase_need(const SyncChunk &ch, SyncShared &sh, uint32_t t)
+{
+    if (!sync_lane_active(ch, t) || t == ch.first_lane) return false;
+    const uint2 e = make_uint2(sh.cur[t - 1].p, sh.cur[t - 1].cz);
+    sh.entry_next[t] = e;
+    return e.x != sh.entry_used[t].x || e.y != sh.entry_used[t].y;
+}
+
+// Phase "round r >= 1" of a lane that needs it. Returns true when the checkpoint was met.
+template <class W>
+B2J_HD bool sync_phase_round(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t)
+{
+    return sync_walk_lane(w, ch, sh, t, sh.entry_next[t], false);
+}
+
+} // namespace b2j
+#endif

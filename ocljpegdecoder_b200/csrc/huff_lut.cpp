@@ -88,6 +88,63 @@ bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
     return out.size() <= max_entries;
 }
 
+bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out)
+{
+    const int K = is_dc ? kWalkBitsDc : kWalkBitsAc;
+    struct Code { uint32_t code; int len; int sym; };
+    Code codes[256];
+    int n = 0;
+    uint32_t code = 0;
+    for (int l = 1; l <= 16; l++)
+    {
+        for (int i = 0; i < counts[l - 1]; i++)
+        {
+            if (n >= 256 || (code >> l)) return false;
+            codes[n].code = code; codes[n].len = l; codes[n].sym = symbols[n];
+            n++; code++;
+        }
+        code <<= 1;
+    }
+    // the codeword (if any) that starts at bit `pos` of the K-bit window w and ends inside it
+    auto match = [&](uint32_t w, int pos) -> const Code * {
+        for (int i = 0; i < n; i++)
+        {
+            const Code &c = codes[i];
+            if (c.len > K - pos) break;   // canonical order: lengths never decrease
+            if (((w >> (K - pos - c.len)) & ((1u << c.len) - 1u)) == c.code) return &c;
+        }
+        return nullptr;
+    };
+    out.assign((size_t)1 << K, 0);
+    for (uint32_t w = 0; w < (1u << K); w++)
+    {
+        if (is_dc)
+        {
+            const Code *c = match(w, 0);
+            if (c && c->sym <= 16) out[w] = (uint16_t)((c->len + c->sym) | (c->sym << 9));
+            continue;
+        }
+        int pos = 0, zadv = 0, nsym = 0, nbits = 0, eob = 0;
+        while (pos < K)
+        {
+            const Code *c = match(w, pos);
+            if (!c) break;
+            if (c->sym == 0x00)   // end of block (decoder.cpp:247-249)
+            {
+                if (zadv + 1 > 63) break;
+                nbits = pos + c->len; eob = 1; nsym++;
+                break;
+            }
+            const int run = c->sym >> 4, size = c->sym & 15;
+            const int adv = run + 1;   // a coefficient behind `run` zeros, or run + 1 zeros when size == 0 (decoder.cpp:250-256)
+            if (zadv + adv > 63 || pos + c->len + size > 31) break;
+            zadv += adv; pos += c->len + size; nbits = pos; nsym++;
+        }
+        if (nsym) out[w] = (uint16_t)(nbits | ((zadv + eob) << 9) | (eob << 15));
+    }
+    return true;
+}
+
 bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out)
 {
     out.assign(kLutHeader, 0);
@@ -109,7 +166,7 @@ bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out)
             if (!found)
             {
                 std::vector<uint16_t> t;
-                if (!build_huff_lut(d.huff_counts[slot], d.huff_symbols[slot], kind == 0, t, kLutMaxEntries)) return false;
+                if (!build_huff_lut(d.huff_counts[slot], d.huff_symbols[slot], kind == 0, t, kLutMaxDecode)) return false;
                 off = (uint32_t)out.size();
                 out.insert(out.end(), t.begin(), t.end());
                 built_slot[nbuilt] = slot; built_off[nbuilt] = off; nbuilt++;
@@ -119,6 +176,33 @@ bool build_lut_set(const b2j_image_desc &d, std::vector<uint16_t> &out)
         }
     }
     while (out.size() & 7) out.push_back(0);   // 16-byte granules for the copy into shared memory
+    if (out.size() > (size_t)kLutMaxDecode) return false;
+    out[12] = (uint16_t)out.size();            // the decode part ends here
+    // walk tables of the self-synchronising path, one per distinct table
+    nbuilt = 0;
+    for (int c = 0; c < 3; c++)
+    {
+        for (int kind = 0; kind < 2; kind++)
+        {
+            const int th = kind == 0 ? (d.huff_id[c] >> 4) : (d.huff_id[c] & 0xF);
+            const int slot = kind * 4 + th;
+            uint32_t off = 0;
+            bool found = false;
+            for (int k = 0; k < nbuilt; k++)
+                if (built_slot[k] == slot) { off = built_off[k]; found = true; }
+            if (!found)
+            {
+                std::vector<uint16_t> t;
+                if (!build_walk_lut(d.huff_counts[slot], d.huff_symbols[slot], kind == 0, t)) return false;
+                off = (uint32_t)out.size();
+                out.insert(out.end(), t.begin(), t.end());
+                built_slot[nbuilt] = slot; built_off[nbuilt] = off; nbuilt++;
+            }
+            if (off >= 0x8000) return false;   // byte offsets of the tables are kept in 16 bits
+            out[6 + kind * 3 + c] = (uint16_t)off;
+        }
+    }
+    while (out.size() & 7) out.push_back(0);
     return out.size() <= (size_t)kLutMaxEntries;
 }
 

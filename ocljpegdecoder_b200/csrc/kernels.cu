@@ -25,6 +25,7 @@
 
 #include "b2j_internal.h"
 #include "b2j_math.h"
+#include "b2j_sync.h"
 #include "kernels.h"
 
 namespace b2j {
@@ -910,7 +911,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t k = tid; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
+        for (uint32_t k = tid; k < im.lut_dec_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
         uint4 *z = reinterpret_cast<uint4 *>(s_slots);
         for (uint32_t k = tid; k < kHuffThreads * 8; k += kHuffThreads) z[k] = make_uint4(0, 0, 0, 0);
         if (tid < 128) s_zz2[tid] = tid < 64 ? c_zigzag2[tid] : (uint8_t)0;
@@ -1121,78 +1122,31 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 //                the last parallel round still changed: correctness does not depend on luck;
 //   scan         exclusive prefix of block counts and DC sums -> first block index and DC predictors;
 //   decode       k_huff_decode<SYNC>: every lane decodes the blocks that START in its sub-sequence.
-struct WalkState { uint32_t p, c, z; };
-
-struct WalkResult
+// The walk itself (walk_stream) lives in b2j_sync.h, shared with the host emulation. Device view of the tables:
+// the LUT set staged in shared memory, addressed through the 32-bit shared window.
+struct DevLut
 {
-    uint32_t p, cz, nblk, fs, fc;
-    int32_t dc0, dc1, dc2;
+    uint32_t sm;            // shared-window byte address of the set
+    const uint16_t *s;      // the same, as a pointer (header reads outside the loops)
+    __device__ __forceinline__ uint32_t at(uint32_t i) const { return lds_u16(sm + (i << 1)); }
+    __device__ __forceinline__ uint32_t hdr(int i) const { return s[i]; }
 };
 
-// Walks the stream from state `s` while the next symbol starts before bit `limit`. No output.
-__device__ __forceinline__ WalkResult walk_subsequence(const uint8_t *__restrict__ base, uint32_t sm_lut, const uint16_t *__restrict__ s_lut,
-                                                       WalkState s, uint32_t limit, uint32_t tot, uint32_t ny)
+struct DevWalk
 {
-    WalkResult r;
-    r.nblk = 0; r.fs = kSubNone; r.fc = 0; r.dc0 = r.dc1 = r.dc2 = 0;
-    uint32_t p = s.p, c = s.c, z = s.z;
-    bool bad = false;
-    if (p < limit)
+    StreamWords stream;
+    DevLut lut;
+    WalkTabs tabs;
+    uint32_t tot, ny;
+    __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_lut, const uint16_t *s_lut, const ImgDev &im)
     {
-        BitReader<1> br;
-        br.init(base, p >> 3);
-        const uint32_t bit0 = br.bitpos;
-        br.bitpos += p & 7u;
-        const uint32_t p_byte = p & ~7u;
-        uint32_t comp = c < ny ? 0u : (c - ny + 1u);
-        // The loop body is one straight path for DC and AC symbols alike (selects instead of branches): the lanes
-        // of a warp sit at unrelated places of their blocks, and a branch taken by a few lanes costs every lane.
-        // Table addresses of the three components, DC in the low half-word, AC in the high one.
-        const uint32_t t0 = (uint32_t)s_lut[0] | ((uint32_t)s_lut[3] << 16), t1 = (uint32_t)s_lut[1] | ((uint32_t)s_lut[4] << 16),
-                       t2 = (uint32_t)s_lut[2] | ((uint32_t)s_lut[5] << 16);
-        while (p < limit)
-        {
-            const uint32_t pk = br.peek();
-            const bool dc = z == 0u;
-            const uint32_t tc = comp == 0u ? t0 : (comp == 1u ? t1 : t2);
-            const uint32_t tab = sm_lut + 2u * (dc ? (tc & 0xFFFFu) : (tc >> 16));
-            const uint32_t bits = dc ? (uint32_t)kLutBitsDc : (uint32_t)kLutBits;
-            uint32_t e = lut_first(tab, pk, bits);
-            if (!(e & 32u))
-            {
-                e = lut_second(tab, pk, e, bits);
-                if (!(e & 32u)) { bad = true; break; }
-            }
-            const uint32_t len = e & 31u;
-            const uint32_t size = (e >> 6) & (dc ? 31u : 15u);
-            // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
-            // (a warp-vote guard around this was measured: slower at every quality)
-            const int32_t diff = dc ? extend_sz(pk << len, size) : 0;
-            const bool first = dc && r.fs == kSubNone;
-            r.fs = first ? p : r.fs;
-            r.fc = first ? c : r.fc;
-            r.nblk += dc ? 1u : 0u;
-            r.dc0 += comp == 0u ? diff : 0;
-            r.dc1 += comp == 1u ? diff : 0;
-            r.dc2 += comp == 2u ? diff : 0;
-            z = dc ? 1u : z + (e >> 10) + 1u;   // AC: zero run + the coefficient (or the extra zero of a size-0 run); EOB: run 63
-            br.bitpos += len + size;
-            br.refill();
-            p = p_byte + br.nref * 32u + br.bitpos - bit0;
-            const bool done = z >= 64u;         // the block is complete: next block of the MCU
-            z = done ? 0u : z;
-            const uint32_t cn = (c + 1u == tot) ? 0u : c + 1u;
-            c = done ? cn : c;
-            comp = c < ny ? 0u : (c - ny + 1u);
-        }
+        stream.w = reinterpret_cast<const uint32_t *>(clean_img);
+        lut.sm = sm_lut; lut.s = s_lut;
+        tabs = walk_tabs(lut);
+        tot = im.tot_blks; ny = im.ny_blks;
     }
-    // A non-code can only be met by a walk that started from a wrong guess (or in a corrupt stream, which
-    // the final decode flags): hand the next lane the same guess a first-round walk would use instead
-    // of a dead state, so that a wrong guess never poisons the records downstream.
-    r.p = bad ? max(p, limit) : p;
-    r.cz = bad ? 0u : (c | (z << 8));
-    return r;
-}
+    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, tabs, s, limit, tot, ny, 1u); }
+};
 
 __device__ __forceinline__ void store_rec(SubRec *__restrict__ dst, const WalkResult &r)
 {
@@ -1245,16 +1199,17 @@ k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, 
     const uint32_t j = cta.seg_first + tid;
     SubRec *rec = recs + im.sub_first;
     uint32_t *stamp = stamps + im.sub_first;
-    const uint8_t *base = clean + im.raw_off;
     SubMid *mid = mids + im.sub_first;
+    DevWalk wk;
+    wk.init(clean + im.raw_off, sm_lut, s_lut, im);
     if (round == 0u)
     {
         if (j >= n_sub) return;
         const uint32_t lo = j * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
         const WalkState s = {lo, 0u, 0u};
-        const WalkResult ra = walk_subsequence(base, sm_lut, s_lut, s, md, im.tot_blks, im.ny_blks);
+        const WalkResult ra = wk.walk(s, md);
         const WalkState sm = {ra.p, ra.cz & 0xFFu, ra.cz >> 8};
-        const WalkResult rb = walk_subsequence(base, sm_lut, s_lut, sm, hi, im.tot_blks, im.ny_blks);
+        const WalkResult rb = wk.walk(sm, hi);
         WalkResult r = rb;   // exit state of the second half
         r.nblk = ra.nblk + rb.nblk; r.dc0 = ra.dc0 + rb.dc0; r.dc1 = ra.dc1 + rb.dc1; r.dc2 = ra.dc2 + rb.dc2;
         if (ra.fs != kSubNone) { r.fs = ra.fs; r.fc = ra.fc; }
@@ -1269,7 +1224,7 @@ k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, 
     const uint2 in = *reinterpret_cast<const uint2 *>(rec + j);
     const uint32_t lo = (j + 1u) * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
     const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-    const WalkResult ra = walk_subsequence(base, sm_lut, s_lut, s, md, im.tot_blks, im.ny_blks);
+    const WalkResult ra = wk.walk(s, md);
     const uint4 m0 = reinterpret_cast<const uint4 *>(mid + j + 1)[0];   // p, cz, nblk, dc0 of the checkpoint
     if (ra.p == m0.x && ra.cz == m0.y)
     {
@@ -1346,8 +1301,9 @@ k_sync_walk_list(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ i
                 const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
                 const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
                 const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-                const WalkResult r = walk_subsequence(clean + im.raw_off, sm_lut, s_lut, s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits),
-                                                      im.tot_blks, im.ny_blks);
+                DevWalk wk;
+                wk.init(clean + im.raw_off, sm_lut, s_lut, im);
+                const WalkResult r = wk.walk(s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits));
                 store_rec(rec + k + 1, r);
                 if (r.p != old.x || r.cz != old.y)
                     sync_flag_changed(ent.x, k + 1u, round, (uint32_t)kSyncRounds, cnt, out_list, stamps + im.sub_first);
@@ -1410,7 +1366,9 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
                     const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
                     const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
                     const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-                    const WalkResult r = walk_subsequence(base, sm_lut, s_lut, s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits), im.tot_blks, im.ny_blks);
+                    DevWalk wk;
+                    wk.init(base, sm_lut, s_lut, im);
+                    const WalkResult r = wk.walk(s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits));
                     store_rec(rec + k + 1, r);
                     stamp[k] = 0u;
                     rewalked++;
@@ -2031,7 +1989,7 @@ size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffTh
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {
-    const int hb = (int)huff_smem_bytes(max_lut_len, true);
+    const int hb = (int)huff_smem_bytes(kLutMaxDecode, true);   // the decode kernels stage the decode part of a LUT set only
     cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_huff_decode<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
@@ -2081,9 +2039,9 @@ void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.cta1 - r.cta0;
     if (n == 0) return;
-    const size_t sm = huff_smem_bytes(a.max_lut_len, false);
+    const size_t sm = huff_smem_bytes(a.max_lut_dec_len, false);
     if (a.huff_variant & 1u)
-        k_huff_decode<true, false, false><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len, true), s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
+        k_huff_decode<true, false, false><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len, true), s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
                                                                     a.coef, a.status, nullptr, nullptr);
     else
         k_huff_decode<false, false, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
@@ -2108,7 +2066,7 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
                                                       a.sync_cnt, a.sync_stats);
     k_sync_cta_totals<<<n, kHuffThreads, 0, s>>>(a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.recs, a.sync_cta_base + r.scta0);
     k_sync_cta_scan<<<ni, 32, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.sync_cta_base + r.scta0, r.scta0);
-    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
+    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
                                                                                            a.clean_len, a.luts, a.coef, a.status, a.recs, a.sync_cta_base + r.scta0);
 }
 

@@ -40,7 +40,7 @@ struct DecodeArgs
     uint8_t *pixels;
     int32_t *status;
     // sizes
-    uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len;
+    uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len, max_lut_dec_len;   // LUT set lengths: whole / decode part
     int out_format;          // B2J_OUT_*: layout of the pixel plane (b2j_batch_set_output_format)
     bool use_tma;
     bool any_wide_q;         // some quantiser of the batch exceeds 255 (16-bit DQT): generic dequantisation

@@ -344,11 +344,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     std::vector<TileDev> tiles;
     std::vector<uint16_t> luts;
     std::vector<uint16_t> qtabs((size_t)n * 192);
-    std::map<std::string, std::pair<uint32_t, uint32_t>> lut_cache;
+    struct LutRef { uint32_t off, len, dec_len; };
+    std::map<std::string, LutRef> lut_cache;
     static const uint8_t zz[64] = B2J_ZIGZAG_TABLE;
 
     size_t raw_total = 0, pix_total = 0, blk_total = 0;
-    uint32_t seg_total = 0, max_lut_len = 0;
+    uint32_t seg_total = 0, max_lut_len = 0, max_lut_dec_len = 0;
     int64_t pixels = 0, scan_bytes = 0;
     int rc = B2J_OK;
     for (int i = 0; i < n && rc == B2J_OK; i++)
@@ -436,11 +437,13 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             if (!build_lut_set(d, set)) { rc = B2J_E_UNSUPPORTED; t_last_error = "Huffman tables need more decode-table space than one CTA has"; break; }
             const uint32_t off = (uint32_t)luts.size();
             luts.insert(luts.end(), set.begin(), set.end());
-            it = lut_cache.emplace(key, std::make_pair(off, (uint32_t)set.size())).first;
+            it = lut_cache.emplace(key, LutRef{off, (uint32_t)set.size(), (uint32_t)set[12]}).first;
         }
-        im.lut_off = it->second.first;
-        im.lut_len = it->second.second;
+        im.lut_off = it->second.off;
+        im.lut_len = it->second.len;
+        im.lut_dec_len = it->second.dec_len;
         if (im.lut_len > max_lut_len) max_lut_len = im.lut_len;
+        if (im.lut_dec_len > max_lut_dec_len) max_lut_dec_len = im.lut_dec_len;
         pixels += (int64_t)d.width * d.height;
         scan_bytes += (int64_t)d.scan_size;
     }
@@ -588,6 +591,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.n_huff_ctas = (uint32_t)ctas.size();
     a.n_tiles = (uint32_t)tiles.size();
     a.max_lut_len = max_lut_len;
+    a.max_lut_dec_len = max_lut_dec_len;
     a.use_tma = ctx->use_tma;
     a.out_format = B2J_OUT_BGRA;
     a.any_wide_q = false;
