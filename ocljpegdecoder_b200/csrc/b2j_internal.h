@@ -30,7 +30,10 @@ constexpr int kLutHeader = 16;           // u16 words of header in front of a LU
                                          //   [12]   length of the decode part of the set (header + decode tables), a multiple of 8
 constexpr int kLutMaxDecode = 12288;     // u16 entries of the decode part of a LUT set (24 KB of shared memory)
 constexpr int kLutMaxEntries = 32768;    // u16 entries of a whole LUT set, walk tables included (64 KB)
-constexpr int kWalkBitsAc = 12;          // index width of the AC walk tables (several symbols per lookup)
+#ifndef B2J_WALK_BITS_AC
+#define B2J_WALK_BITS_AC 11
+#endif
+constexpr int kWalkBitsAc = B2J_WALK_BITS_AC;   // index width of the AC walk tables (several symbols per lookup)
 constexpr int kWalkBitsDc = 9;           // index width of the DC walk tables
 constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
 constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
@@ -46,19 +49,23 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //   escape  : bits 0-5  = extra index bits nb (1..16 - primary width, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
 //             offset relative to the end of the primary table, in units of kLutSubAlign entries
 //   invalid : 0 (no codeword has this prefix)
-// Walk table entry (u16), used by the walks of the self-synchronising path only (they need no coefficient values):
-//   AC : the symbols whose CODES lie completely inside the next kWalkBitsAc bits, up to and including an end-of-block:
-//        bits 0-4 = bits consumed by all of them (codes + value bits, <= 31), bits 9-14 = scan positions they need
-//        (sum of run + 1, plus 1 when the last of them is the end-of-block symbol: the block must not be complete
-//        in front of it; <= 63), bit 15 = the last one is the end-of-block symbol. A step is valid where
-//        position + bits 9-14 <= 64 (a block that fills up without an end-of-block code ends a group early)
-//   DC : one symbol: bits 0-4 = code length + category, bits 9-13 = category (0..16)
+// Walk tables, used by the walks of the self-synchronising path only (they need no coefficient values):
+//   AC : 32-bit entries. The symbols whose CODES lie completely inside the next kWalkBitsAc bits, up to and including
+//        an end-of-block, form a group. Two 12-bit field sets, the group (bits 0-11) and its first symbol (bits 12-23):
+//          bits 0-4  bits consumed (codes + value bits, <= 31)
+//          bits 5-10 scan positions needed: sum of run + 1, plus 1 when the set ends with the end-of-block symbol
+//                    (the block must not be complete in front of it); <= 63
+//          bit  11   the set ends with the end-of-block symbol
+//        so that position + (bits 5-11) >= 64 exactly when the block is complete behind the set. The group is valid
+//        where position + (bits 5-10) <= 64; a block that fills up without an end-of-block code ends inside a group,
+//        then the first symbol is taken alone.
+//   DC : 16-bit entries, one symbol: bits 0-4 = code length + category, bits 5-9 = category (0..16)
 //   0  : take the one-symbol path through the decode tables (code longer than the index, no codeword, category > 16)
 constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table
 
 // sampling layouts the colour kernel knows (luma h x v with 1x1 chroma)
-enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3, kModeGray = 4 };   // gray: one component
+enum SamplingMode : uint32_t { kMode444 = 0, kMode420 = 1, kMode422 = 2, kMode440 = 3, kModeGray = 4, kModeGeneric = 5 };   // gray: one component; generic: any other layout
 
 // Per-image record in device memory.
 struct ImgDev
@@ -83,6 +90,8 @@ struct ImgDev
     uint32_t mode;         // SamplingMode
     uint32_t tot_blks;     // blocks per MCU
     uint32_t ny_blks;      // luma blocks per MCU
+    uint32_t nu_blks;      // blocks of the second component per MCU
+    uint32_t samp;         // sampling factors, one nibble each: yh | yv<<4 | uh<<8 | uv<<12 | vh<<16 | vv<<20
     uint32_t yh;           // luma blocks per MCU row
     uint32_t wide_q;       // 1 when some quantiser value exceeds 255
     uint32_t sub_first;    // self-synchronising path (streams without DRI): first sub-sequence record of this image

@@ -45,9 +45,9 @@ struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 v = {x, y}; return v; }
 #endif
 
-// host emulation only: counts walk-table steps [0] and one-symbol steps [1]
+// host emulation only: counts AC steps: whole groups [0], first symbol of a group [1], through the decode tables [2]
 #if defined(B2J_WALK_STATS) && !defined(__CUDACC__)
-extern uint64_t g_b2j_walk_steps[2];
+extern uint64_t g_b2j_walk_steps[3];
 #define B2J_WALK_COUNT(k) (g_b2j_walk_steps[k]++)
 #else
 #define B2J_WALK_COUNT(k) ((void)0)
@@ -175,10 +175,12 @@ B2J_HD uint32_t lookup_symbol(const LUT &lut, uint32_t tab, uint32_t pk, uint32_
 // loops of decoder.cpp:286-346) and ends in its state at the first symbol boundary at or behind `limit`, however the
 // symbols were grouped on the way: an AC walk-table step covers several symbols at once, and is taken only while the
 // walk is more than kWalkBitsAc - 1 bits in front of `limit` (every symbol of a group starts inside the index window)
-// and the block cannot fill up in front of the group's last symbol; otherwise, and wherever the walk table has no
-// entry, one symbol is taken through the decode tables.
+// and the block cannot fill up in front of the group's last symbol; otherwise the first symbol of the group is taken
+// alone, and where the walk table has no entry, one symbol goes through the decode tables.
 // From any state -- true or guessed -- the result is a function of that state alone, which is all the
 // synchronisation needs (a guessed walk that reaches a state of the true walk continues exactly like it).
+// Shape: per block one DC step, then AC steps until the block is complete. On the device the lanes of a warp meet again
+// behind every block, so the DC step and the table switch run with all lanes active (they are long, the AC step is short).
 // nu: blocks of component 1 per MCU (component = (c >= ny) + (c >= ny + nu)).
 template <class LUT>
 B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const WalkTabs &tabs, WalkState s, uint32_t limit,
@@ -195,59 +197,69 @@ B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const W
         br.bitpos += p & 7u;
         const uint32_t lim_group = limit > (uint32_t)kWalkBitsAc ? limit - (uint32_t)(kWalkBitsAc - 1) : 0u;
         const uint32_t nyu = ny + nu;
-        uint32_t comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
-        uint32_t tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
-        uint32_t tdc = tw & 0xFFFFu, tac = tw >> 16;
         while (p < limit)
         {
-            const uint32_t pk = br.peek();
-            const bool dc = z == 0u;
-            // one lookup for either kind of symbol
-            const uint32_t e = lut.at((dc ? tdc : tac) + (pk >> (dc ? 32u - (uint32_t)kWalkBitsDc : 32u - (uint32_t)kWalkBitsAc)));
-            uint32_t nb, f;
-            // a group is taken whole only in front of the limit and where the block cannot fill up inside it
-            if (e != 0u && p < lim_group && z + ((e >> 9) & 63u) <= 64u)
+            const uint32_t comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
+            const uint32_t tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
+            if (z == 0u)
             {
-                nb = e & 31u;     // bits this step consumes
-                f = e >> 9;       // AC: scan positions advanced (+ 64 when the group ends the block); DC: category
-                B2J_WALK_COUNT(0);
-            }
-            else
-            {
-                B2J_WALK_COUNT(1);
-                const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
-                const uint32_t e1 = dc ? lookup_symbol(lut, td & 0xFFFFu, pk, (uint32_t)kLutBitsDc) : lookup_symbol(lut, td >> 16, pk, (uint32_t)kLutBits);
-                if (e1 == 0u) { bad = true; break; }
-                const uint32_t size = (e1 >> 6) & (dc ? 31u : 15u);
-                nb = (e1 & 31u) + size;
-                f = dc ? size : (e1 >> 10) + 1u;   // AC: zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
-            }
-            uint32_t zn = z + f;
-            if (dc)
-            {
-                // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
-                const int32_t diff = extend_bits(pk << (nb - f), f);
-#ifdef B2J_WALK_DEBUG
-                fprintf(stderr, "  walk dc p %u nb %u f %u e %x diff %d comp %u\n", p, nb, f, e, diff, comp);
-#endif
+                // ---- DC: starts a block: count it, remember the first one, add its difference to the component's sum
+                const uint32_t pk = br.peek();
+                uint32_t e = lut.at((tw & 0xFFFFu) + (pk >> (32u - (uint32_t)kWalkBitsDc)));
+                uint32_t nb = e & 31u, size = e >> 5;
+                if (e == 0u)
+                {
+                    const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
+                    e = lookup_symbol(lut, td & 0xFFFFu, pk, (uint32_t)kLutBitsDc);
+                    if (e == 0u) { bad = true; break; }
+                    size = (e >> 6) & 31u;
+                    nb = (e & 31u) + size;
+                }
+                const int32_t diff = extend_bits(pk << (nb - size), size);
                 if (r.nblk == 0u) { r.fs = p; r.fc = c; }
                 r.nblk++;
                 r.dc0 += comp == 0u ? diff : 0;
                 r.dc1 += comp == 1u ? diff : 0;
                 r.dc2 += comp == 2u ? diff : 0;
-                zn = 1u;
+                z = 1u;
+                p += nb;
+                br.skip(nb);
             }
-            z = zn;
-            p += nb;
-            br.skip(nb);
+            // ---- AC steps until the block is complete (or the walk ends)
+            const uint32_t tac = tw >> 16;
+            while (z < 64u && p < limit)
+            {
+                const uint32_t pk = br.peek();
+                const uint32_t e = lut.at32(tac + 2u * (pk >> (32u - (uint32_t)kWalkBitsAc)));
+                uint32_t nb, f;
+                if (e != 0u)
+                {
+                    // the whole group where it fits, else its first symbol
+                    const bool group = p < lim_group && z + ((e >> 5) & 63u) <= 64u;
+                    const uint32_t ee = group ? e : e >> 12;
+                    nb = ee & 31u;             // bits consumed
+                    f = (ee >> 5) & 127u;      // scan positions advanced; >= 64 with the end-of-block flag
+                    B2J_WALK_COUNT(group ? 0 : 1);
+                }
+                else
+                {
+                    B2J_WALK_COUNT(2);
+                    const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
+                    const uint32_t e1 = lookup_symbol(lut, td >> 16, pk, (uint32_t)kLutBits);
+                    if (e1 == 0u) { bad = true; break; }
+                    nb = (e1 & 31u) + ((e1 >> 6) & 15u);
+                    f = (e1 >> 10) + 1u;       // zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
+                }
+                z += f;
+                p += nb;
+                br.skip(nb);
+            }
+            if (bad) break;
             if (z >= 64u)
             {
                 // the block is complete: next block of the MCU
                 z = 0u;
                 c = (c + 1u == tot) ? 0u : c + 1u;
-                comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
-                tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
-                tdc = tw & 0xFFFFu; tac = tw >> 16;
             }
         }
     }
@@ -266,7 +278,6 @@ struct SyncShared
     SubMid mid[kHuffThreads];       // round 0: state at the middle + the second half's contribution
     uint2 r0_exit[kHuffThreads];    // round 0: exit state (p, cz) -- stands whenever a later walk meets the checkpoint
     uint2 entry_used[kHuffThreads]; // the entry state (p, cz) cur[] was computed from
-    uint2 entry_next[kHuffThreads]; // round r: the entry state to start from (the predecessor's exit state before the round)
 };
 
 // What a chunk is, for every lane alike.
@@ -346,20 +357,21 @@ B2J_HD void sync_phase_round0(const W &w, const SyncChunk &ch, SyncShared &sh, u
     sync_walk_lane(w, ch, sh, t, entry, true);
 }
 
-// Phase "need" of lane t: does the lane have to walk again? (reads the predecessor's exit state BEFORE the round)
-B2J_HD bool sync_phase_need(const SyncChunk &ch, SyncShared &sh, uint32_t t)
+// Phase "need" of lane t: does the lane have to walk again? Reads the predecessor's exit state BEFORE the round
+// (a barrier separates this phase from the next one) and hands it back in `entry`.
+B2J_HD bool sync_phase_need(const SyncChunk &ch, const SyncShared &sh, uint32_t t, uint2 &entry)
 {
+    entry = make_uint2(0u, 0u);
     if (!sync_lane_active(ch, t) || t == ch.first_lane) return false;
-    const uint2 e = make_uint2(sh.cur[t - 1].p, sh.cur[t - 1].cz);
-    sh.entry_next[t] = e;
-    return e.x != sh.entry_used[t].x || e.y != sh.entry_used[t].y;
+    entry = make_uint2(sh.cur[t - 1].p, sh.cur[t - 1].cz);
+    return entry.x != sh.entry_used[t].x || entry.y != sh.entry_used[t].y;
 }
 
 // Phase "round r >= 1" of a lane that needs it. Returns true when the checkpoint was met.
 template <class W>
-B2J_HD bool sync_phase_round(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t)
+B2J_HD bool sync_phase_round(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, uint2 entry)
 {
-    return sync_walk_lane(w, ch, sh, t, sh.entry_next[t], false);
+    return sync_walk_lane(w, ch, sh, t, entry, false);
 }
 
 } // namespace b2j

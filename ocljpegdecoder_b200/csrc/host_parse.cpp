@@ -138,11 +138,20 @@ int check_gate(const b2j_image_desc &d, int gate)
         if (td > 3 || ta > 3 || !d.huff_present[td] || !d.huff_present[4 + ta]) return B2J_E_UNSUPPORTED;
     }
     if (d.color_space == B2J_CS_GRAY) return B2J_OK;   // admitted by parse_sof0 under B2J_GATE_GRAY only
-    if (d.sampling[1] != 0x11 || d.sampling[2] != 0x11) return B2J_E_UNSUPPORTED;
     const int y = d.sampling[0];
-    if (y == 0x22 || y == 0x11) return B2J_OK;
-    if (gate == B2J_GATE_EXTENDED && (y == 0x21 || y == 0x12)) return B2J_OK;
-    return B2J_E_UNSUPPORTED;
+    if (d.sampling[1] == 0x11 && d.sampling[2] == 0x11 && (y == 0x22 || y == 0x11)) return B2J_OK;   // decoder.cpp:58-69
+    if (gate != B2J_GATE_EXTENDED) return B2J_E_UNSUPPORTED;
+    // extended: any luma sampling with chroma factors that divide it, at most 10 blocks per MCU (ITU T.81 B.2.3)
+    const int yh = y >> 4, yv = y & 0xF;
+    if (yh < 1 || yh > 4 || yv < 1 || yv > 4) return B2J_E_UNSUPPORTED;
+    int tot = yh * yv;
+    for (int c = 1; c < 3; c++)
+    {
+        const int h = d.sampling[c] >> 4, v = d.sampling[c] & 0xF;
+        if (h < 1 || v < 1 || yh % h || yv % v) return B2J_E_UNSUPPORTED;
+        tot += h * v;
+    }
+    return tot <= 10 ? B2J_OK : B2J_E_UNSUPPORTED;
 }
 
 // decoder.cpp:161-192

@@ -115,32 +115,43 @@ bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
         }
         return nullptr;
     };
-    out.assign((size_t)1 << K, 0);
-    for (uint32_t w = 0; w < (1u << K); w++)
+    if (is_dc)
     {
-        if (is_dc)
+        out.assign((size_t)1 << K, 0);
+        for (uint32_t w = 0; w < (1u << K); w++)
         {
             const Code *c = match(w, 0);
-            if (c && c->sym <= 16) out[w] = (uint16_t)((c->len + c->sym) | (c->sym << 9));
-            continue;
+            if (c && c->sym <= 16) out[w] = (uint16_t)((c->len + c->sym) | (c->sym << 5));
         }
+        return true;
+    }
+    // AC: 32-bit entries, stored as two u16 each (little endian): set 0 = the whole group, set 1 = its first symbol
+    out.assign((size_t)2 << K, 0);
+    for (uint32_t w = 0; w < (1u << K); w++)
+    {
         int pos = 0, zadv = 0, nsym = 0, nbits = 0, eob = 0;
+        uint32_t first = 0;
         while (pos < K)
         {
             const Code *c = match(w, pos);
             if (!c) break;
-            if (c->sym == 0x00)   // end of block (decoder.cpp:247-249)
+            int adv, bits, e = 0;
+            if (c->sym == 0x00) { adv = 0; bits = c->len; e = 1; }   // end of block (decoder.cpp:247-249)
+            else
             {
-                if (zadv + 1 > 63) break;
-                nbits = pos + c->len; eob = 1; nsym++;
-                break;
+                adv = (c->sym >> 4) + 1;   // a coefficient behind `run` zeros, or run + 1 zeros when size == 0 (decoder.cpp:250-256)
+                bits = c->len + (c->sym & 15);
             }
-            const int run = c->sym >> 4, size = c->sym & 15;
-            const int adv = run + 1;   // a coefficient behind `run` zeros, or run + 1 zeros when size == 0 (decoder.cpp:250-256)
-            if (zadv + adv > 63 || pos + c->len + size > 31) break;
-            zadv += adv; pos += c->len + size; nbits = pos; nsym++;
+            if (zadv + adv + e > 63 || pos + bits > 31) break;
+            zadv += adv; pos += bits; nbits = pos; eob = e; nsym++;
+            if (nsym == 1) first = (uint32_t)nbits | (uint32_t)(zadv + eob) << 5 | (uint32_t)eob << 11;
+            if (e) break;
         }
-        if (nsym) out[w] = (uint16_t)(nbits | ((zadv + eob) << 9) | (eob << 15));
+        if (!nsym) continue;
+        const uint32_t group = (uint32_t)nbits | (uint32_t)(zadv + eob) << 5 | (uint32_t)eob << 11;
+        const uint32_t v = group | first << 12;
+        out[2 * w] = (uint16_t)v;
+        out[2 * w + 1] = (uint16_t)(v >> 16);
     }
     return true;
 }

@@ -918,7 +918,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     }
     __syncthreads();
 
-    const uint32_t tot = im.tot_blks, ny = im.ny_blks;
+    const uint32_t tot = im.tot_blks, ny = im.ny_blks, nyu = im.ny_blks + im.nu_blks;
     const uint32_t seg = cta.seg_first + tid;
     uint32_t start = 0, end = 0, nblk = 0, blk0 = 0, start_bit = 0, bi = 0;
     int32_t dc0 = 0, dc1 = 0, dc2 = 0;
@@ -944,7 +944,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         const uint32_t bits = clean_len[cta.img] * 8u;
         const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-        active = seg < n_sub;
+        active = seg < n_sub && tid < (uint32_t)kSyncLanes;   // a decode CTA covers one chunk of the synchronisation
         SubRec rec;
         rec.nblk = 0; rec.dc[0] = rec.dc[1] = rec.dc[2] = 0;
         if (active) rec = recs[im.sub_first + seg];
@@ -1008,7 +1008,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     // bi: block index inside the MCU (!SYNC: uniform across the warp, segments start on MCU boundaries)
     for (uint32_t b = 0; b < max_nblk; b++)
     {
-        const uint32_t comp = bi < ny ? 0u : (bi - ny + 1u);
+        const uint32_t comp = (bi >= ny ? 1u : 0u) + (bi >= nyu ? 1u : 0u);
         const uint32_t dc_tab = sm_lut + 2u * (uint32_t)s_lut[comp];
         const uint32_t ac_tab = sm_lut + 2u * (uint32_t)s_lut[3 + comp];
         const bool mine = b < nblk;
@@ -1110,18 +1110,15 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 // The clean stream of an image is cut into sub-sequences of kSubBytes*8 bits, one lane each. A JPEG
 // decoder state is (bit position, block index inside the MCU, zig-zag position); Huffman codes
 // self-synchronise, so a lane that starts from a GUESSED state at its sub-sequence border usually
-// falls into step with the true decoder within a few dozen symbols. Passes:
-//   round 0      every lane walks its own sub-sequence from the guess (border, block 0, DC expected)
-//                and records its exit state;
-//   round r >= 1 lane j walks sub-sequence j+1 from the recorded exit state of j and replaces the
-//                record of j+1 (exit state AND the block count / DC sums / first block start seen
-//                on the way). Round 1 does this for all j, later rounds only where the input state
-//                changed in the previous round. Record 0 starts from the true state, so record k is
-//                true after at most k rounds -- in practice after one or two;
-//   sweep        one warp per image runs over the records once more, in order, and repairs whatever
-//                the last parallel round still changed: correctness does not depend on luck;
-//   scan         exclusive prefix of block counts and DC sums -> first block index and DC predictors;
-//   decode       k_huff_decode<SYNC>: every lane decodes the blocks that START in its sub-sequence.
+// falls into step with the true decoder within a few dozen symbols. Kernels:
+//   k_sync_chunks   one CTA per chunk of kSyncLanes sub-sequences: round 0 and all further rounds of the chunk in
+//                   shared memory (b2j_sync.h), records + chunk totals + chunk entry/exit state out;
+//   k_sync_sweep    one CTA per image: every chunk must have started from its predecessor's exit state; the rare
+//                   chunk that did not is run again, in order, with its entry forced -- correctness does not
+//                   depend on luck;
+//   k_sync_cta_scan exclusive prefix of block counts and DC sums over the chunks -> first block index and DC
+//                   predictors of every chunk;
+//   k_huff_decode<SYNC>  every lane decodes the blocks that START in its sub-sequence.
 // The walk itself (walk_stream) lives in b2j_sync.h, shared with the host emulation. Device view of the tables:
 // the LUT set staged in shared memory, addressed through the 32-bit shared window.
 struct DevLut
@@ -1129,6 +1126,7 @@ struct DevLut
     uint32_t sm;            // shared-window byte address of the set
     const uint16_t *s;      // the same, as a pointer (header reads outside the loops)
     __device__ __forceinline__ uint32_t at(uint32_t i) const { return lds_u16(sm + (i << 1)); }
+    __device__ __forceinline__ uint32_t at32(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm + (i << 1))); return v; }
     __device__ __forceinline__ uint32_t hdr(int i) const { return s[i]; }
 };
 
@@ -1137,272 +1135,51 @@ struct DevWalk
     StreamWords stream;
     DevLut lut;
     WalkTabs tabs;
-    uint32_t tot, ny;
+    uint32_t tot, ny, nu;
     __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_lut, const uint16_t *s_lut, const ImgDev &im)
     {
         stream.w = reinterpret_cast<const uint32_t *>(clean_img);
         lut.sm = sm_lut; lut.s = s_lut;
         tabs = walk_tabs(lut);
-        tot = im.tot_blks; ny = im.ny_blks;
+        tot = im.tot_blks; ny = im.ny_blks; nu = im.nu_blks;
     }
-    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, tabs, s, limit, tot, ny, 1u); }
+    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, tabs, s, limit, tot, ny, nu); }
 };
 
-__device__ __forceinline__ void store_rec(SubRec *__restrict__ dst, const WalkResult &r)
-{
-    uint4 a, b;
-    a.x = r.p; a.y = r.cz; a.z = r.nblk; a.w = (uint32_t)r.dc0;
-    b.x = (uint32_t)r.dc1; b.y = (uint32_t)r.dc2; b.z = r.fs; b.w = r.fc;
-    reinterpret_cast<uint4 *>(dst)[0] = a;
-    reinterpret_cast<uint4 *>(dst)[1] = b;
-}
+// ---- chunk-wise synchronisation (b2j_sync.h): all rounds of a chunk of kSyncLanes sub-sequences inside one CTA.
+// Shared memory: [ SyncShared ][ LUT set ].
+constexpr uint32_t kSyncSharedBytes = (sizeof(SyncShared) + 15u) & ~15u;
 
-// Appends sub-sequence k of image img to the work list of the next round (its exit state has just changed).
-__device__ __forceinline__ void sync_flag_changed(uint32_t img, uint32_t k, uint32_t round, uint32_t last_round, uint32_t *__restrict__ cnt,
-                                                  uint2 *__restrict__ out_list, uint32_t *__restrict__ stamp)
+// Runs one chunk (round 0, the rounds, output). All threads of the CTA; `wk` walks this image's stream.
+// chunk_state[k] = (entry state assumed for the first lane, exit state of the last lane); cta_tot[k] = totals of the chunk.
+__device__ __forceinline__ void sync_run_chunk(const DevWalk &wk, SyncShared &sh, const SyncChunk &ch, SubRec *__restrict__ rec_img,
+                                               uint4 *chunk_state_k, uint4 *cta_tot_k, uint32_t *__restrict__ stats, uint4 *s_wtot)
 {
-    const uint32_t slot = atomicAdd(&cnt[round], 1u);   // also the convergence evidence: exit states this round still changed
-    out_list[slot] = make_uint2(img, k);
-    if (round == last_round) stamp[k] = round;          // what the sequential sweep repairs
-}
-
-// Rounds 0 and 1, one lane per sub-sequence.
-// round 0: lane j walks sub-sequence j from the guessed state, in two halves: the state at the first symbol at or
-//          behind the middle of the sub-sequence and what the second half contributes are kept as a checkpoint.
-// round 1: lane j walks sub-sequence j+1 from the exit state recorded for j, but only up to the middle. A decoder
-//          that started from a wrong guess falls into step with the true one within a few dozen symbols, so nearly
-//          always the lane arrives at exactly the checkpointed state: the second half of round 0 stands, the record
-//          is the lane's first half plus the checkpoint's second half and the exit state does not change. A lane
-//          that does not meet the checkpoint puts its sub-sequence on the work list of round 2 (full walk).
-// Half a pass over the stream instead of a whole one for round 1.
-__global__ void __launch_bounds__(kHuffThreads)
-k_sync_walk(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
-            const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
-            SubMid *__restrict__ mids, uint32_t *__restrict__ stamps, uint32_t round, uint32_t *__restrict__ cnt, uint2 *__restrict__ out_list)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
-    const uint32_t tid = threadIdx.x;
-    const HuffCtaDev cta = ctas[blockIdx.x];
-    const ImgDev &im = imgs[cta.img];
-    const uint32_t bits = clean_len[cta.img] * 8u;
-    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-    if (cta.seg_first >= n_sub) return;   // uniform: the clean stream is shorter than the raw bound
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t k = tid; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
-    }
-    __syncthreads();
-    uint32_t sm_lut;
-    asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
-    const uint32_t j = cta.seg_first + tid;
-    SubRec *rec = recs + im.sub_first;
-    uint32_t *stamp = stamps + im.sub_first;
-    SubMid *mid = mids + im.sub_first;
-    DevWalk wk;
-    wk.init(clean + im.raw_off, sm_lut, s_lut, im);
-    if (round == 0u)
-    {
-        if (j >= n_sub) return;
-        const uint32_t lo = j * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
-        const WalkState s = {lo, 0u, 0u};
-        const WalkResult ra = wk.walk(s, md);
-        const WalkState sm = {ra.p, ra.cz & 0xFFu, ra.cz >> 8};
-        const WalkResult rb = wk.walk(sm, hi);
-        WalkResult r = rb;   // exit state of the second half
-        r.nblk = ra.nblk + rb.nblk; r.dc0 = ra.dc0 + rb.dc0; r.dc1 = ra.dc1 + rb.dc1; r.dc2 = ra.dc2 + rb.dc2;
-        if (ra.fs != kSubNone) { r.fs = ra.fs; r.fc = ra.fc; }
-        store_rec(rec + j, r);
-        WalkResult m = rb;   // checkpoint: state at the middle + the second half's contribution
-        m.p = ra.p; m.cz = ra.cz;
-        store_rec(reinterpret_cast<SubRec *>(mid + j), m);
-        stamp[j] = 0u;
-        return;
-    }
-    if (j + 1u >= n_sub) return;
-    const uint2 in = *reinterpret_cast<const uint2 *>(rec + j);
-    const uint32_t lo = (j + 1u) * (uint32_t)(kSubBytes * 8), hi = min(lo + (uint32_t)(kSubBytes * 8), bits), md = min(lo + (uint32_t)(kSubBytes * 4), hi);
-    const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-    const WalkResult ra = wk.walk(s, md);
-    const uint4 m0 = reinterpret_cast<const uint4 *>(mid + j + 1)[0];   // p, cz, nblk, dc0 of the checkpoint
-    if (ra.p == m0.x && ra.cz == m0.y)
-    {
-        const uint4 m1 = reinterpret_cast<const uint4 *>(mid + j + 1)[1];   // dc1, dc2, fs, fc
-        const uint2 ex = *reinterpret_cast<const uint2 *>(rec + j + 1);      // exit state: stands
-        WalkResult r;
-        r.p = ex.x; r.cz = ex.y;
-        r.nblk = ra.nblk + m0.z; r.dc0 = ra.dc0 + (int32_t)m0.w; r.dc1 = ra.dc1 + (int32_t)m1.x; r.dc2 = ra.dc2 + (int32_t)m1.y;
-        r.fs = ra.fs != kSubNone ? ra.fs : m1.z;
-        r.fc = ra.fs != kSubNone ? ra.fc : m1.w;
-        store_rec(rec + j + 1, r);
-    }
-    else
-    {
-        // not in step at the middle: full walk of sub-sequence j+1 in round 2 (entry j = "walk j+1 from the record of j")
-        const uint32_t slot = atomicAdd(&cnt[round], 1u);
-        out_list[slot] = make_uint2(cta.img, j);
-    }
-}
-
-// Rounds >= 2 touch few sub-sequences, scattered over the whole batch: they run over the compact work list
-// the previous round wrote, one lane per entry, instead of over all sub-sequences (where a warp with one
-// lane due costs as much as a full one). Entry (img, k): the exit state of sub-sequence k changed, so k+1 is
-// walked again from it. Lanes of a CTA may belong to images with different decode tables: the CTA serves one
-// table set at a time (usually there is only one).
-__global__ void __launch_bounds__(kHuffThreads)
-k_sync_walk_list(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ clean_len,
-                 const uint16_t *__restrict__ luts, SubRec *__restrict__ recs, uint32_t *__restrict__ stamps, uint32_t round,
-                 uint32_t *__restrict__ cnt, const uint2 *__restrict__ in_list, uint2 *__restrict__ out_list)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
-    __shared__ uint32_t s_pick, s_len;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t count = cnt[round - 1u];
-    uint32_t sm_lut;
-    asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
-    uint32_t staged = 0xFFFFFFFFu;
-    for (uint32_t first = blockIdx.x * kHuffThreads; first < count; first += gridDim.x * kHuffThreads)   // uniform for the CTA
-    {
-        const uint32_t t = first + tid;
-        uint2 ent = make_uint2(0u, 0u);
-        uint32_t my_lut = 0xFFFFFFFFu, n_sub = 0u, bits = 0u;
-        if (t < count)
-        {
-            ent = in_list[t];
-            bits = clean_len[ent.x] * 8u;
-            n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-            if (ent.y + 1u < n_sub) my_lut = imgs[ent.x].lut_off;
-        }
-        while (true)
-        {
-            if (tid == 0) s_pick = 0xFFFFFFFFu;
-            __syncthreads();
-            if (my_lut != 0xFFFFFFFFu) atomicMin(&s_pick, my_lut);
-            __syncthreads();
-            const uint32_t pick = s_pick;
-            if (pick == 0xFFFFFFFFu) break;   // every entry of this batch is done (uniform)
-            if (pick != staged)
-            {
-                if (my_lut == pick) s_len = imgs[ent.x].lut_len;
-                __syncthreads();
-                const uint4 *src = reinterpret_cast<const uint4 *>(luts + pick);
-                uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-                for (uint32_t q = tid; q < s_len / 8; q += kHuffThreads) dst[q] = __ldg(src + q);
-                staged = pick;
-                __syncthreads();
-            }
-            if (my_lut == pick)
-            {
-                const ImgDev &im = imgs[ent.x];
-                const uint32_t k = ent.y;
-                SubRec *rec = recs + im.sub_first;
-                const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
-                const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
-                const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-                DevWalk wk;
-                wk.init(clean + im.raw_off, sm_lut, s_lut, im);
-                const WalkResult r = wk.walk(s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits));
-                store_rec(rec + k + 1, r);
-                if (r.p != old.x || r.cz != old.y)
-                    sync_flag_changed(ent.x, k + 1u, round, (uint32_t)kSyncRounds, cnt, out_list, stamps + im.sub_first);
-                my_lut = 0xFFFFFFFFu;
-            }
-            __syncthreads();   // the tables may be replaced in the next turn
-        }
-    }
-}
-
-// One CTA per image: in-order repair of whatever the last parallel round still changed (stamp == last_round).
-// All threads look for stamps, one thread chases each change downstream until the stored state is reproduced.
-// Also folds the per-round counters into the batch's convergence statistics.
-constexpr int kSweepThreads = 256;
-__global__ void __launch_bounds__(kSweepThreads)
-k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
-             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
-             uint32_t *__restrict__ stamps, uint32_t last_round, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ stats)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
-    __shared__ uint8_t s_flag[kSweepThreads];
-    const uint32_t tid = threadIdx.x;
-    if (blockIdx.x == 0 && tid >= 1u && tid <= last_round && cnt[tid]) atomicAdd(&stats[tid], cnt[tid]);
-    if (cnt[last_round] == 0u) return;   // converged before the last round: nothing to repair (uniform for the grid)
-    const uint32_t img = sync_imgs[blockIdx.x];
-    const ImgDev &im = imgs[img];
-    const uint32_t bits = clean_len[img] * 8u;
-    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-    SubRec *rec = recs + im.sub_first;
-    uint32_t *stamp = stamps + im.sub_first;
-    const uint8_t *base = clean + im.raw_off;
-    bool lut_ready = false;
-    uint32_t sm_lut = 0, rewalked = 0;
-    for (uint32_t b0 = 0; b0 + 1u < n_sub; b0 += kSweepThreads)
-    {
-        const uint32_t j = b0 + tid;
-        const bool flag = j + 1u < n_sub && stamp[j] == last_round;
-        if (!__syncthreads_or(flag)) continue;
-        if (!lut_ready)
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
-            uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-            for (uint32_t k = tid; k < im.lut_len / 8; k += kSweepThreads) dst[k] = __ldg(src + k);
-            asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem)));
-            lut_ready = true;
-        }
-        s_flag[tid] = flag ? 1 : 0;
-        __syncthreads();
-        if (tid == 0)
-        {
-            for (uint32_t t = 0; t < (uint32_t)kSweepThreads; t++)
-            {
-                if (!s_flag[t]) continue;
-                uint32_t k = b0 + t;
-                if (stamp[k] != last_round) continue;   // an earlier chase already passed over it
-                // chase the change downstream until the stored state is reproduced
-                while (k + 1u < n_sub)
-                {
-                    const uint2 in = *reinterpret_cast<const uint2 *>(rec + k);
-                    const uint2 old = *reinterpret_cast<const uint2 *>(rec + k + 1);
-                    const WalkState s = {in.x, in.y & 0xFFu, in.y >> 8};
-                    DevWalk wk;
-                    wk.init(base, sm_lut, s_lut, im);
-                    const WalkResult r = wk.walk(s, min((k + 2u) * (uint32_t)(kSubBytes * 8), bits));
-                    store_rec(rec + k + 1, r);
-                    stamp[k] = 0u;
-                    rewalked++;
-                    if (r.p == old.x && r.cz == old.y) break;
-                    k++;
-                }
-            }
-        }
-        __syncthreads();   // cleared stamps are visible to the next chunk's readers
-    }
-    if (tid == 0 && rewalked) atomicAdd(&stats[7], rewalked);   // sub-sequences re-walked by the sequential sweep
-}
-
-// Prefix of (blocks started, DC sums) over the sub-sequence records of an image, in two small steps: the totals
-// of every decode CTA (128 consecutive records, read coalesced), then one warp per image turns the CTA totals
-// into exclusive bases. The lanes of k_huff_decode<SYNC> add the part inside their CTA themselves.
-__global__ void __launch_bounds__(kHuffThreads)
-k_sync_cta_totals(const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas, const uint32_t *__restrict__ clean_len,
-                  const SubRec *__restrict__ recs, uint4 *__restrict__ cta_tot)
-{
-    __shared__ uint4 s_w[kHuffThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const HuffCtaDev cta = ctas[blockIdx.x];
-    const ImgDev &im = imgs[cta.img];
-    const uint32_t bits = clean_len[cta.img] * 8u;
-    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
-    const uint32_t j = cta.seg_first + tid;
-    uint32_t nb = 0; int32_t d0 = 0, d1 = 0, d2 = 0;
-    if (j < n_sub)
+    sync_phase_round0(wk, ch, sh, tid);
+    __syncthreads();
+    for (uint32_t round = 1; round <= (uint32_t)kHuffThreads + 1u; round++)   // lane k of a chunk is final after k rounds
     {
-        const SubRec *rec = recs + im.sub_first + j;
-        const uint4 a = reinterpret_cast<const uint4 *>(rec)[0];
-        const uint2 b = reinterpret_cast<const uint2 *>(rec)[2];
-        nb = a.z; d0 = (int32_t)a.w; d1 = (int32_t)b.x; d2 = (int32_t)b.y;
+        uint2 entry;
+        const bool need = sync_phase_need(ch, sh, tid, entry);
+        if (!__syncthreads_or(need)) break;   // also orders the reads of cur[] above before the writes below
+        bool met = true;
+        if (need) met = sync_phase_round(wk, ch, sh, tid, entry);
+        const int missed = __syncthreads_count(need && !met);
+        if (tid == 0 && missed && stats) atomicAdd(&stats[round < 6u ? round : 6u], (uint32_t)missed);
+    }
+    // ---- output: the records of the chunk's own lanes, its totals, its entry and exit state
+    const bool out = tid >= (uint32_t)kSyncPre && sync_lane_active(ch, tid);
+    uint32_t nb = 0; int32_t d0 = 0, d1 = 0, d2 = 0;
+    if (out)
+    {
+        const SubRec c = sh.cur[tid];
+        uint4 a, b;
+        a.x = c.p; a.y = c.cz; a.z = c.nblk; a.w = (uint32_t)c.dc[0];
+        b.x = (uint32_t)c.dc[1]; b.y = (uint32_t)c.dc[2]; b.z = c.fs; b.w = c.fc;
+        uint4 *dst = reinterpret_cast<uint4 *>(rec_img + sync_lane_sub(ch, tid));
+        dst[0] = a; dst[1] = b;
+        nb = c.nblk; d0 = c.dc[0]; d1 = c.dc[1]; d2 = c.dc[2];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -1410,15 +1187,132 @@ k_sync_cta_totals(const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict_
         nb += __shfl_xor_sync(0xFFFFFFFFu, nb, o); d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, o);
         d1 += __shfl_xor_sync(0xFFFFFFFFu, d1, o); d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
     }
-    if (lane == 0) s_w[tid >> 5] = make_uint4(nb, (uint32_t)d0, (uint32_t)d1, (uint32_t)d2);
+    if (lane == 0) s_wtot[tid >> 5] = make_uint4(nb, (uint32_t)d0, (uint32_t)d1, (uint32_t)d2);
     __syncthreads();
     if (tid == 0)
     {
-        uint4 t = s_w[0];
+        uint4 t = s_wtot[0];
 #pragma unroll
-        for (int w = 1; w < kHuffThreads / 32; w++) { t.x += s_w[w].x; t.y += s_w[w].y; t.z += s_w[w].z; t.w += s_w[w].w; }
-        cta_tot[blockIdx.x] = t;
+        for (int w = 1; w < kHuffThreads / 32; w++) { t.x += s_wtot[w].x; t.y += s_wtot[w].y; t.z += s_wtot[w].z; t.w += s_wtot[w].w; }
+        *cta_tot_k = t;
+        const uint32_t n_out = min((uint32_t)kSyncLanes, ch.n_sub - ch.first);
+        const uint32_t last = (uint32_t)kSyncPre + n_out - 1u;
+        *chunk_state_k = make_uint4(sh.entry_used[kSyncPre].x, sh.entry_used[kSyncPre].y, sh.cur[last].p, sh.cur[last].cz);
     }
+    __syncthreads();   // s_wtot and sh may be reused by the caller
+}
+
+__device__ __forceinline__ void sync_stage_lut(uint16_t *s_lut, const uint16_t *__restrict__ luts, const ImgDev &im)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    for (uint32_t k = threadIdx.x; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
+}
+
+// One CTA per chunk. use_pre: walk kSyncPre sub-sequences in front of the chunk to find its entry state (0: every chunk
+// but the first starts from the bare guess, so that every border is repaired by the sweep -- a test knob).
+__global__ void __launch_bounds__(kHuffThreads)
+k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
+              const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
+              uint4 *__restrict__ chunk_state, uint4 *__restrict__ cta_tot, uint32_t *__restrict__ stats, uint32_t use_pre)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint4 s_wtot[kHuffThreads / 32];
+    SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
+    const HuffCtaDev cta = ctas[blockIdx.x];
+    const ImgDev &im = imgs[cta.img];
+    const uint32_t bits = clean_len[cta.img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    if (cta.seg_first >= n_sub)
+    {
+        // uniform: the clean stream is shorter than the raw bound; the chunk contributes nothing
+        if (threadIdx.x == 0) { cta_tot[blockIdx.x] = make_uint4(0u, 0u, 0u, 0u); chunk_state[blockIdx.x] = make_uint4(0u, 0u, 0u, 0u); }
+        return;
+    }
+    sync_stage_lut(s_lut, luts, im);
+    __syncthreads();
+    uint32_t sm_lut;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
+    DevWalk wk;
+    wk.init(clean + im.raw_off, sm_lut, s_lut, im);
+    SyncChunk ch;
+    ch.first = cta.seg_first; ch.n_sub = n_sub; ch.bits = bits; ch.tot = im.tot_blks; ch.ny = im.ny_blks;
+    const bool pre = use_pre != 0u && cta.seg_first != 0u;
+    ch.first_lane = pre ? (cta.seg_first >= (uint32_t)kSyncPre ? 0u : (uint32_t)kSyncPre - cta.seg_first) : (uint32_t)kSyncPre;
+    ch.forced = cta.seg_first == 0u;          // the first chunk of an image starts from the true state
+    ch.forced_entry = make_uint2(0u, 0u);
+    sync_run_chunk(wk, sh, ch, recs + im.sub_first, chunk_state + blockIdx.x, cta_tot + blockIdx.x, stats, s_wtot);
+}
+
+// One CTA per image: every chunk must have started from the state its predecessor ended in. All threads compare; the
+// first chunk that does not is run again with its entry forced, then the search goes on behind it (its exit state may have
+// changed). With pre-lanes this finds nothing in almost every image and costs one pass over the chunk states.
+__global__ void __launch_bounds__(kHuffThreads)
+k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
+             const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
+             uint4 *chunk_state, uint4 *cta_tot, uint32_t *__restrict__ stats, uint32_t scta0)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint4 s_wtot[kHuffThreads / 32];
+    __shared__ uint32_t s_min;
+    SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t img = sync_imgs[blockIdx.x];
+    const ImgDev &im = imgs[img];
+    const uint32_t bits = clean_len[img] * 8u;
+    const uint32_t n_sub = (bits + kSubBytes * 8 - 1) / (kSubBytes * 8);
+    const uint32_t nc = (n_sub + (uint32_t)kSyncLanes - 1u) / (uint32_t)kSyncLanes;
+    uint4 *state = chunk_state + (im.scta_first - scta0);
+    uint4 *tot = cta_tot + (im.scta_first - scta0);
+    bool lut_ready = false;
+    uint32_t c_start = 1u, repaired = 0u;
+    while (c_start < nc)
+    {
+        // the first chunk at or behind c_start whose entry state is not its predecessor's exit state
+        uint32_t found = nc;
+        for (uint32_t base = c_start; base < nc; base += kHuffThreads)
+        {
+            const uint32_t c = base + tid;
+            bool bad = false;
+            if (c < nc)
+            {
+                const uint4 mine = __ldcg(state + c), prev = __ldcg(state + c - 1u);
+                bad = mine.x != prev.z || mine.y != prev.w;
+            }
+            if (!__syncthreads_or(bad)) continue;
+            if (tid == 0) s_min = nc;
+            __syncthreads();
+            if (bad) atomicMin(&s_min, c);
+            __syncthreads();
+            found = s_min;
+            break;
+        }
+        if (found >= nc) break;
+        if (!lut_ready)
+        {
+            sync_stage_lut(s_lut, luts, im);
+            lut_ready = true;
+        }
+        __syncthreads();
+        uint32_t sm_lut;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
+        DevWalk wk;
+        wk.init(clean + im.raw_off, sm_lut, s_lut, im);
+        const uint4 prev = __ldcg(state + found - 1u);
+        SyncChunk ch;
+        ch.first = found * (uint32_t)kSyncLanes; ch.n_sub = n_sub; ch.bits = bits; ch.tot = im.tot_blks; ch.ny = im.ny_blks;
+        ch.first_lane = (uint32_t)kSyncPre;
+        ch.forced = true;
+        ch.forced_entry = make_uint2(prev.z, prev.w);
+        sync_run_chunk(wk, sh, ch, recs + im.sub_first, state + found, tot + found, nullptr, s_wtot);
+        __threadfence_block();
+        __syncthreads();
+        repaired++;
+        c_start = found + 1u;
+    }
+    if (tid == 0 && repaired) atomicAdd(&stats[7], repaired);   // chunks whose pre-lanes had not fallen into step
 }
 
 // One warp per image: exclusive scan of its CTA totals (in place: totals in, bases out).
@@ -1427,7 +1321,7 @@ k_sync_cta_scan(const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sy
 {
     const uint32_t lane = threadIdx.x;
     const ImgDev &im = imgs[sync_imgs[blockIdx.x]];
-    const uint32_t n = (im.n_sub_max + kHuffThreads - 1u) / kHuffThreads;
+    const uint32_t n = (im.n_sub_max + (uint32_t)kSyncLanes - 1u) / (uint32_t)kSyncLanes;
     uint4 *t = cta_tot + (im.scta_first - scta0);
     uint4 run = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t b0 = 0; b0 < n; b0 += 32u)
@@ -1518,6 +1412,7 @@ struct TileSide
     uint8_t *pix;                             // first byte of the image in the pixel plane
     uint32_t width, height;
     uint32_t mode, n_mcus;
+    uint32_t samp;                            // kModeGeneric: sampling factors, one nibble each: yh | yv<<4 | uh<<8 | uv<<12 | vh<<16 | vv<<20
 };
 
 struct TileSmem
@@ -1749,10 +1644,23 @@ __device__ __forceinline__ int32_t dp2a_hi(uint32_t a, uint32_t b)
 template <int RH, int RV, bool NARROWQ>
 __device__ __forceinline__ void idct_phase(uint8_t *__restrict__ tilep, const TileSide &sd)
 {
-    using G = TileGeom<RH, RV>;
+    using G = TileGeom<(RH > 0 ? RH : 1), (RV > 0 ? RV : 1)>;
     const uint32_t tid = threadIdx.x;
-    const uint32_t bi = tid % G::tot;
-    const uint32_t comp = RH == 0 ? 0u : (bi < G::ny ? 0u : (bi - G::ny + 1u));   // RH == 0: one-component image
+    uint32_t comp;
+    if (RH == 0) comp = 0u;                   // one-component image
+    else if (RH < 0)
+    {
+        // any other layout (kModeGeneric): block counts of the components from the sampling factors
+        const uint32_t sp = sd.samp;
+        const uint32_t ny = (sp & 15u) * ((sp >> 4) & 15u), nu = ((sp >> 8) & 15u) * ((sp >> 12) & 15u), nv = ((sp >> 16) & 15u) * ((sp >> 20) & 15u);
+        const uint32_t bi = tid % (ny + nu + nv);
+        comp = (bi >= ny ? 1u : 0u) + (bi >= ny + nu ? 1u : 0u);
+    }
+    else
+    {
+        const uint32_t bi = tid % G::tot;
+        comp = bi < G::ny ? 0u : (bi - G::ny + 1u);
+    }
     const uint32_t *q = sd.qt + comp * kQtStride;
     uint8_t *rowp = tilep + tid * 128u;
     const uint32_t sw = tid & 7u;
@@ -1845,6 +1753,53 @@ __device__ __forceinline__ void csc_gray(const uint8_t *__restrict__ s_tile, con
     }
 }
 
+// Any other layout (kModeGeneric): luma h x v with chroma components whose factors divide the
+// luma's -- 4:1:1 (41,11,11), 14, 31, 42, ..., and components with several blocks per MCU (22,21,21). The reference's
+// generic loop (decoder.cpp:474-483), one 4-pixel group per work item, one pixel at a time: rare layouts, kept simple.
+template <int FMT>
+__device__ __forceinline__ void csc_generic(const uint8_t *__restrict__ s_tile, const TileSide &sd, uint32_t tid)
+{
+    const uint32_t sp = sd.samp;
+    const uint32_t yh = sp & 15u, yv = (sp >> 4) & 15u, uh = (sp >> 8) & 15u, uv = (sp >> 12) & 15u, vh = (sp >> 16) & 15u, vv = (sp >> 20) & 15u;
+    const uint32_t ny = yh * yv, nu = uh * uv, tot = ny + nu + vh * vv;
+    const uint32_t mcu_w = 8u * yh, mcu_h = 8u * yv, xg = mcu_w / 4u, items = mcu_h * xg;
+    const uint32_t ruh = yh / uh, ruv = yv / uv, rvh = yh / vh, rvv = yv / vv;
+    const uint32_t width = sd.width, height = sd.height;
+    const bool vec_ok = (width & 3u) == 0u;
+    constexpr uint32_t bpp = FMT == B2J_OUT_BGRA ? 4u : (FMT == B2J_OUT_RGB24 ? 3u : 1u);
+    const size_t pitch = (size_t)width * bpp, plane = (size_t)width * height;
+    for (uint32_t it = tid; it < sd.n_mcus * items; it += kTileBlocks)
+    {
+        const uint32_t m = it / items, r = it % items, y = r / xg, x = (r % xg) * 4u;
+        const uint2 mxy = sd.mcu_xy[m];
+        const uint32_t px = mxy.x * mcu_w + x, py = mxy.y * mcu_h + y;
+        if (px >= width || py >= height) continue;
+        const uint32_t row0 = m * tot;
+        uint32_t rgb[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++)
+        {
+            const uint32_t xx = x + k;
+            const uint32_t yb = row0 + (y >> 3) * yh + (xx >> 3);
+            const uint32_t ux = xx / ruh, uy = y / ruv, vx = xx / rvh, vy = y / rvv;
+            const uint32_t ub = row0 + ny + (uy >> 3) * uh + (ux >> 3), vb = row0 + ny + nu + (vy >> 3) * vh + (vx >> 3);
+            const uint32_t Y = *reinterpret_cast<const uint16_t *>(s_tile + yb * 128u + (((y & 7u) ^ (yb & 7u)) << 4) + (xx & 7u) * 2u);
+            const uint32_t U = *reinterpret_cast<const uint16_t *>(s_tile + ub * 128u + (((uy & 7u) ^ (ub & 7u)) << 4) + (ux & 7u) * 2u);
+            const uint32_t V = *reinterpret_cast<const uint16_t *>(s_tile + vb * 128u + (((vy & 7u) ^ (vb & 7u)) << 4) + (vx & 7u) * 2u);
+            rgb[k] = csc_pixel_biased((int32_t)Y, (int32_t)U, (int32_t)V);   // R << 16 | G << 8 | B
+        }
+        uint32_t R[2], Gc[2], B[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+            R[h] = (rgb[2 * h] >> 16) | (rgb[2 * h + 1] >> 16) << 16;
+            Gc[h] = ((rgb[2 * h] >> 8) & 0xFFu) | ((rgb[2 * h + 1] >> 8) & 0xFFu) << 16;
+            B[h] = (rgb[2 * h] & 0xFFu) | (rgb[2 * h + 1] & 0xFFu) << 16;
+        }
+        store_pixels4<FMT>(sd.pix + ((size_t)py * width + px) * bpp, plane, px, width, vec_ok, R, Gc, B);
+    }
+}
+
 template <int FMT>
 __device__ __forceinline__ void csc_dispatch(const uint8_t *tilep, const TileSide &sd)
 {
@@ -1860,7 +1815,7 @@ __device__ __forceinline__ void csc_dispatch(const uint8_t *tilep, const TileSid
 
 // Side data of a tile, in two halves so that the global loads of the first half can fly while the
 // previous tile is being transformed.
-struct SideRegs { uint32_t q, width, height, mcu_count_w; uint64_t pix_off; };
+struct SideRegs { uint32_t q, width, height, mcu_count_w, samp; uint64_t pix_off; };
 
 __device__ __forceinline__ SideRegs side_load(const ImgDev *__restrict__ imgs, const uint16_t *__restrict__ qtabs, const TileDev d)
 {
@@ -1870,6 +1825,7 @@ __device__ __forceinline__ SideRegs side_load(const ImgDev *__restrict__ imgs, c
     r.width = __ldg(&im->width);
     r.height = __ldg(&im->height);
     r.mcu_count_w = __ldg(&im->mcu_count_w);
+    r.samp = __ldg(&im->samp);
     r.pix_off = __ldg(reinterpret_cast<const unsigned long long *>(&im->pix_off));
     return r;
 }
@@ -1896,6 +1852,7 @@ __device__ __forceinline__ void side_store(TileSide &sd, const TileDev d, const 
         sd.pix = pix + r.pix_off;
         sd.width = r.width; sd.height = r.height;
         sd.mode = d.info & 0xFFu; sd.n_mcus = n_mcus;
+        sd.samp = r.samp;
     }
 }
 
@@ -1913,7 +1870,9 @@ __device__ __forceinline__ uint32_t mode_tot(uint32_t mode) { return mode == kMo
 // GRAY: the kernel for the tiles of one-component images (B2J_GATE_GRAY). A kernel of its own over a tile range of
 // its own (the host sorts a part's tiles by kind), because merely carrying the extra paths, or a test for them at
 // the top of the kernel, slows the colour kernel down by 2 % (measured).
-template <bool USE_TMA, bool NARROWQ, int FMT, bool GRAY = false>
+// KIND: kTileColour (the four everyday layouts), kTileGray, kTileGeneric (any other layout: csc_generic).
+constexpr int kTileColour = 0, kTileGray = 1, kTileGeneric = 2;
+template <bool USE_TMA, bool NARROWQ, int FMT, int KIND = kTileColour>
 __global__ void __launch_bounds__(kTileBlocks, B2J_IDCT_MIN_CTAS)
 k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs,
            const TileDev *__restrict__ tiles, const uint16_t *__restrict__ qtabs, uint8_t *__restrict__ pix, int32_t *__restrict__ status)
@@ -1955,11 +1914,17 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
         side_store<NARROWQ>(sm.side[0], d, r, pix);
         __syncthreads();
     }
-    if (GRAY)
+    if (KIND == kTileGray)
     {
         idct_phase<0, 0, NARROWQ>(sm.tile[0], sm.side[0]);
         __syncthreads();
         csc_gray<FMT>(sm.tile[0], sm.side[0], tid);
+    }
+    else if (KIND == kTileGeneric)
+    {
+        idct_phase<-1, -1, NARROWQ>(sm.tile[0], sm.side[0]);
+        __syncthreads();
+        csc_generic<FMT>(sm.tile[0], sm.side[0], tid);
     }
     else
     {
@@ -1973,13 +1938,13 @@ k_idct_csc(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__
 // Coefficient tap: int16 quantised plane -> the reference's int32 dequantised mcu_data layout.
 __global__ void __launch_bounds__(256)
 k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qtab, uint32_t blk_count,
-               uint32_t tot, uint32_t ny, int32_t *__restrict__ out)
+               uint32_t tot, uint32_t ny, uint32_t nu, int32_t *__restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)blk_count * 64) return;
     const uint32_t blk = (uint32_t)(i >> 6), k = (uint32_t)(i & 63);
     const uint32_t bi = blk % tot;
-    const uint32_t comp = bi < ny ? 0u : (bi - ny + 1u);
+    const uint32_t comp = (bi >= ny ? 1u : 0u) + (bi >= ny + nu ? 1u : 0u);
     out[i] = (int32_t)coef[i] * (int32_t)qtab[comp * 64 + k];
 }
 
@@ -1996,11 +1961,9 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_huff_decode<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sync_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
+    e = cudaFuncSetAttribute(k_sync_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSyncSharedBytes + max_lut_len * 2));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sync_walk_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_lut_len * 2);
+    e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSyncSharedBytes + max_lut_len * 2));
     if (e != cudaSuccess) return e;
 #define B2J_IDCT_ATTR(T, Q, F) \
     e = cudaFuncSetAttribute(k_idct_csc<T, Q, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
@@ -2011,7 +1974,9 @@ cudaError_t configure_kernels(uint32_t max_lut_len)
     B2J_IDCT_ATTR(true, true, B2J_OUT_RGB_PLANAR) B2J_IDCT_ATTR(true, false, B2J_OUT_RGB_PLANAR)
 #undef B2J_IDCT_ATTR
 #define B2J_IDCT_ATTR(Q, F) \
-    e = cudaFuncSetAttribute(k_idct_csc<true, Q, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
+    e = cudaFuncSetAttribute(k_idct_csc<true, Q, F, kTileGray>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
+    if (e != cudaSuccess) return e; \
+    e = cudaFuncSetAttribute(k_idct_csc<true, Q, F, kTileGeneric>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes); \
     if (e != cudaSuccess) return e;
     B2J_IDCT_ATTR(true, B2J_OUT_BGRA) B2J_IDCT_ATTR(false, B2J_OUT_BGRA) B2J_IDCT_ATTR(true, B2J_OUT_RGB24) B2J_IDCT_ATTR(false, B2J_OUT_RGB24)
     B2J_IDCT_ATTR(true, B2J_OUT_RGB_PLANAR) B2J_IDCT_ATTR(false, B2J_OUT_RGB_PLANAR)
@@ -2048,23 +2013,16 @@ void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
                                                                      a.coef, a.status, nullptr, nullptr);
 }
 
-// Streams without restart markers: kSyncRounds + 1 walk passes, the sweep, the scan, then the decode.
+// Streams without restart markers: chunk-wise synchronisation, the sweep, the scan, then the decode.
 void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.scta1 - r.scta0, ni = r.simg1 - r.simg0;
     if (n == 0 || ni == 0) return;
-    const size_t lut_bytes = (size_t)a.max_lut_len * 2;
-    cudaMemsetAsync(a.sync_cnt, 0, 4 * 8, s);   // per launch sequence: the counters also index the work lists
-    // rounds 0 and 1 over all sub-sequences, rounds 2.. over the work list of the round before (lists alternate)
-    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.mids, a.stamps, 0u, a.sync_cnt, a.sync_list[1]);
-    k_sync_walk<<<n, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.mids, a.stamps, 1u, a.sync_cnt, a.sync_list[1]);
-    const uint32_t list_ctas = n < 592u ? n : 592u;   // 4 CTAs per SM walk the list with a grid stride
-    for (uint32_t round = 2; round <= (uint32_t)kSyncRounds; round++)
-        k_sync_walk_list<<<list_ctas, kHuffThreads, lut_bytes, s>>>(a.clean, a.imgs, a.clean_len, a.luts, a.recs, a.stamps, round, a.sync_cnt,
-                                                                    a.sync_list[(round - 1u) & 1u], a.sync_list[round & 1u]);
-    k_sync_sweep<<<ni, kSweepThreads, lut_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.stamps, (uint32_t)kSyncRounds,
-                                                      a.sync_cnt, a.sync_stats);
-    k_sync_cta_totals<<<n, kHuffThreads, 0, s>>>(a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.recs, a.sync_cta_base + r.scta0);
+    const size_t sync_bytes = kSyncSharedBytes + (size_t)a.max_lut_len * 2;
+    k_sync_chunks<<<n, kHuffThreads, sync_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.sync_chunk_state + r.scta0,
+                                                      a.sync_cta_base + r.scta0, a.sync_stats, a.sync_use_pre ? 1u : 0u);
+    k_sync_sweep<<<ni, kHuffThreads, sync_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.sync_chunk_state + r.scta0,
+                                                     a.sync_cta_base + r.scta0, a.sync_stats, r.scta0);
     k_sync_cta_scan<<<ni, 32, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.sync_cta_base + r.scta0, r.scta0);
     k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
                                                                                            a.clean_len, a.luts, a.coef, a.status, a.recs, a.sync_cta_base + r.scta0);
@@ -2072,31 +2030,32 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
 
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
-    const uint32_t nc = r.tile_mid - r.tile0, ng = r.tile1 - r.tile_mid;
-#define B2J_IDCT_LAUNCH(T, Q, F, G) k_idct_csc<T, Q, F, G><<<(G) ? ng : nc, kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, \
-        a.tiles + ((G) ? r.tile_mid : r.tile0), a.qtabs, a.pixels, a.status)
-    if (nc)
+    // a part's tiles are sorted by kind: [tile0, tile_mid) the four everyday layouts, [tile_mid, tile_gen) one-component
+    // images, [tile_gen, tile1) every other layout
+    const uint32_t first[3] = {r.tile0, r.tile_mid, r.tile_gen}, count[3] = {r.tile_mid - r.tile0, r.tile_gen - r.tile_mid, r.tile1 - r.tile_gen};
+#define B2J_IDCT_LAUNCH(T, Q, F, K) k_idct_csc<T, Q, F, K><<<count[K], kTileBlocks, kTileSmemBytes, s>>>(*a.tmap, a.coef, a.imgs, \
+        a.tiles + first[K], a.qtabs, a.pixels, a.status)
+#define B2J_IDCT_BY_FORMAT(K) \
+    if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24, K); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24, K); } \
+    else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR, K); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR, K); } \
+    else { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA, K); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA, K); }
+    if (count[kTileColour])
     {
-        // the other output formats exist for the TMA variant only (B2J_USE_TMA=0 is a measurement knob of the BGRA path)
-        if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24, false); }
-        else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR, false); }
-        else if (a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA, false); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA, false); }
-        else { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false, B2J_OUT_BGRA, false); else B2J_IDCT_LAUNCH(false, true, B2J_OUT_BGRA, false); }
+        // B2J_USE_TMA=0 is a measurement knob of the BGRA path: plain vector loads instead of the tensor-map load
+        if (a.out_format == B2J_OUT_BGRA && !a.use_tma) { if (a.any_wide_q) B2J_IDCT_LAUNCH(false, false, B2J_OUT_BGRA, kTileColour); else B2J_IDCT_LAUNCH(false, true, B2J_OUT_BGRA, kTileColour); }
+        else { B2J_IDCT_BY_FORMAT(kTileColour) }
     }
-    if (ng)
-    {
-        if (a.out_format == B2J_OUT_RGB24) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB24, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB24, true); }
-        else if (a.out_format == B2J_OUT_RGB_PLANAR) { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_RGB_PLANAR, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_RGB_PLANAR, true); }
-        else { if (a.any_wide_q) B2J_IDCT_LAUNCH(true, false, B2J_OUT_BGRA, true); else B2J_IDCT_LAUNCH(true, true, B2J_OUT_BGRA, true); }
-    }
+    if (count[kTileGray]) { B2J_IDCT_BY_FORMAT(kTileGray) }
+    if (count[kTileGeneric]) { B2J_IDCT_BY_FORMAT(kTileGeneric) }
+#undef B2J_IDCT_BY_FORMAT
 #undef B2J_IDCT_LAUNCH
 }
 
-void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s)
+void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, uint32_t nu, int32_t *out, cudaStream_t s)
 {
     const size_t n = (size_t)blk_count * 64;
     if (!n) return;
-    k_expand_coefs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(coef, qtab, blk_count, tot, ny, out);
+    k_expand_coefs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(coef, qtab, blk_count, tot, ny, nu, out);
 }
 
 } // namespace b2j

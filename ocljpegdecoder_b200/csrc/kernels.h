@@ -28,13 +28,11 @@ struct DecodeArgs
     uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;   // three-kernel pre-pass (B2J_PREPASS=3)
     uint64_t *chunk_state;   // single-pass pre-pass: look-back words, zeroed before every decode
     uint32_t *clean_len, *seg_start;
-    SubRec *recs;       // self-synchronising path: one record per sub-sequence
-    SubMid *mids;       // round-0 checkpoints at the middle of every sub-sequence
-    uint4 *sync_cta_base;   // per decode CTA of the self-synchronising path: (blocks started, DC sums) in front of it
-    uint32_t *stamps;
-    uint32_t *sync_stats;   // [r] = exit states changed in round r, [7] = sub-sequences re-walked by the sweep
-    uint32_t *sync_cnt;     // the same counters for the launch sequence in flight: they index the work lists
-    uint2 *sync_list[2];    // work lists of the rounds >= 2 (image, sub-sequence), written by one round, read by the next
+    SubRec *recs;           // self-synchronising path: one record per sub-sequence
+    uint4 *sync_cta_base;   // per chunk (= decode CTA) of the self-synchronising path: (blocks started, DC sums), then their prefix
+    uint4 *sync_chunk_state;   // per chunk: entry state it assumed (x, y), exit state (z, w)
+    uint32_t *sync_stats;   // [r] = lanes that walked again in round r without meeting their checkpoint (r >= 6 in [6]), [7] = chunks the sweep re-ran
+    bool sync_use_pre;      // pre-lanes on (default); off (B2J_SYNC_PRE=0): every chunk border is repaired by the sweep (test knob)
     // outputs
     int16_t *coef;
     uint8_t *pixels;
@@ -49,18 +47,19 @@ struct DecodeArgs
 };
 
 // A contiguous group of images of a batch: the unit the two-stream pipeline works on.
-// Tiles of a part: [tile0, tile_mid) belong to three-component images, [tile_mid, tile1) to one-component images.
-struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1, scta0, scta1, simg0, simg1, tile_mid; };
+// Tiles of a part, sorted by kind: [tile0, tile_mid) the four everyday colour layouts, [tile_mid, tile_gen) one-component images,
+// [tile_gen, tile1) every other layout (kModeGeneric).
+struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1, scta0, scta1, simg0, simg1, tile_mid, tile_gen; };
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
 size_t huff_smem_bytes(uint32_t max_lut_len, bool ring);
 void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
-void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // kSyncRounds + 5 kernels
-constexpr int kSyncLaunches = kSyncRounds + 5;
+void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 4 kernels
+constexpr int kSyncLaunches = 4;
 void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s);      // 1 kernel
-void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, int32_t *out, cudaStream_t s);
+void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, uint32_t nu, int32_t *out, cudaStream_t s);
 
 } // namespace b2j
 #endif

@@ -112,7 +112,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_stamps, off_sync_stats, off_chunk_state, off_sync_cnt, off_sync_list, off_mids;
+    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -153,13 +153,15 @@ int make_tensor_map(b2j_ctx *ctx, b2j_batch *b)
 
 uint32_t mode_of(const b2j_image_desc &d)
 {
-    if (d.tot_blks_per_mcu == 1) return kModeGray;
+    if (d.color_space == B2J_CS_GRAY) return kModeGray;
+    if (d.sampling[1] != 0x11 || d.sampling[2] != 0x11) return kModeGeneric;
     switch (d.sampling[0])
     {
     case 0x11: return kMode444;
     case 0x22: return kMode420;
     case 0x21: return kMode422;
-    default: return kMode440;
+    case 0x12: return kMode440;
+    default: return kModeGeneric;
     }
 }
 
@@ -178,6 +180,9 @@ bool geometry_ok(const b2j_image_desc &d)
         blks[c] = h * v; tot += h * v;
     }
     if (tot > 10) return false;
+    // the kernels replicate chroma samples: the chroma factors must divide the luma's (what the gate admits)
+    for (int c = 1; c < (gray ? 1 : 3); c++)
+        if ((d.sampling[0] >> 4) % (d.sampling[c] >> 4) || (d.sampling[0] & 0xF) % (d.sampling[c] & 0xF)) return false;
     const int mcw = (d.width - 1) / (8 * mh) + 1, mch = (d.height - 1) / (8 * mv) + 1;
     if (d.mcu_width != 8 * mh || d.mcu_height != 8 * mv || d.mcu_count_w != mcw || d.mcu_count_h != mch) return false;
     if (d.mcu_count != mcw * mch || d.tot_blks_per_mcu != tot || d.blk_count != d.mcu_count * tot) return false;
@@ -388,7 +393,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             im.n_sub_max = (im.raw_len + kSubBytes - 1) / kSubBytes;
             if (im.n_sub_max == 0) im.n_sub_max = 1;
             sub_total += im.n_sub_max;
-            for (uint32_t s = 0; s < im.n_sub_max; s += kHuffThreads) sctas.push_back({(uint32_t)i, s});
+            for (uint32_t s = 0; s < im.n_sub_max; s += kSyncLanes) sctas.push_back({(uint32_t)i, s});   // one chunk per CTA
             simgs.push_back((uint32_t)i);
         }
         im.blk_first = (uint32_t)blk_total;
@@ -399,6 +404,9 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         im.mode = mode_of(d);
         im.tot_blks = (uint32_t)d.tot_blks_per_mcu;
         im.ny_blks = (uint32_t)d.blks_per_mcu[0];
+        im.nu_blks = (uint32_t)d.blks_per_mcu[1];
+        im.samp = (uint32_t)(d.sampling[0] >> 4) | (uint32_t)(d.sampling[0] & 0xF) << 4 | (uint32_t)(d.sampling[1] >> 4) << 8 |
+                  (uint32_t)(d.sampling[1] & 0xF) << 12 | (uint32_t)(d.sampling[2] >> 4) << 16 | (uint32_t)(d.sampling[2] & 0xF) << 20;
         im.yh = (uint32_t)(d.sampling[0] >> 4);
         const uint32_t mcus_per_tile = kTileBlocks / im.tot_blks;
         for (uint32_t m = 0; m < im.mcu_count; m += mcus_per_tile)
@@ -463,12 +471,14 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
             if (p == np - 1) i1 = n;
             b->parts.push_back({(uint32_t)i0, (uint32_t)i1, img_chunk0[(size_t)i0], img_chunk0[(size_t)i1], img_cta0[(size_t)i0], img_cta0[(size_t)i1],
                                 img_tile0[(size_t)i0], img_tile0[(size_t)i1], img_scta0[(size_t)i0], img_scta0[(size_t)i1],
-                                img_simg0[(size_t)i0], img_simg0[(size_t)i1], 0u});
+                                img_simg0[(size_t)i0], img_simg0[(size_t)i1], 0u, 0u});
             // the tiles of one-component images go behind the others: they have a kernel of their own
             PartRange &pr = b->parts.back();
             auto mid = std::stable_partition(tiles.begin() + pr.tile0, tiles.begin() + pr.tile1,
-                                             [](const TileDev &t) { return (t.info & 0xFFu) != kModeGray; });
+                                             [](const TileDev &t) { return (t.info & 0xFFu) < kModeGray; });
+            auto gen = std::stable_partition(mid, tiles.begin() + pr.tile1, [](const TileDev &t) { return (t.info & 0xFFu) == kModeGray; });
             pr.tile_mid = (uint32_t)(mid - tiles.begin());
+            pr.tile_gen = (uint32_t)(gen - tiles.begin());
             i0 = i1;
         }
         b->ev_huff.resize(b->parts.size());
@@ -508,11 +518,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_status = place(4 * (size_t)n);
     b->off_recs = place(sizeof(SubRec) * (size_t)sub_total);
     b->off_pres = place(sizeof(uint4) * (sctas.size() + 1));
-    b->off_stamps = place(4 * (size_t)sub_total);
     b->off_sync_stats = place(4 * 8);
-    b->off_sync_cnt = place(4 * 8);
-    b->off_mids = place(sizeof(SubMid) * (size_t)sub_total);
-    b->off_sync_list = place(2 * sizeof(uint2) * (size_t)sub_total);
+    b->off_chunk_states = place(sizeof(uint4) * (sctas.size() + 1));
     b->off_chunk_state = place(8 * chunk_img.size());
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
@@ -565,12 +572,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.sync_imgs = reinterpret_cast<const uint32_t *>(b->d_blob + b->off_simgs);
     a.recs = reinterpret_cast<SubRec *>(b->d_scratch + b->off_recs);
     a.sync_cta_base = reinterpret_cast<uint4 *>(b->d_scratch + b->off_pres);
-    a.stamps = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_stamps);
     a.sync_stats = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_stats);
-    a.sync_cnt = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_sync_cnt);
-    a.mids = reinterpret_cast<SubMid *>(b->d_scratch + b->off_mids);
-    a.sync_list[0] = reinterpret_cast<uint2 *>(b->d_scratch + b->off_sync_list);
-    a.sync_list[1] = a.sync_list[0] + sub_total;
+    a.sync_chunk_state = reinterpret_cast<uint4 *>(b->d_scratch + b->off_chunk_states);
     a.tiles = reinterpret_cast<const TileDev *>(b->d_blob + b->off_tiles);
     a.luts = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_luts);
     a.qtabs = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_qtabs);
@@ -601,13 +604,15 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         a.prepass_fused = !(pp && atoi(pp) == 3);
         const char *hv = getenv("B2J_HUFF_VARIANT");
         a.huff_variant = hv ? (uint32_t)atoi(hv) : 0u;
+        const char *sp = getenv("B2J_SYNC_PRE");
+        a.sync_use_pre = !(sp && atoi(sp) == 0);
     }
 
     b2j_batch_info &inf = b->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_images = n;
     int idct_launches = 0;
-    for (const PartRange &pr : b->parts) idct_launches += (pr.tile_mid > pr.tile0 ? 1 : 0) + (pr.tile1 > pr.tile_mid ? 1 : 0);
+    for (const PartRange &pr : b->parts) idct_launches += (pr.tile_mid > pr.tile0 ? 1 : 0) + (pr.tile_gen > pr.tile_mid ? 1 : 0) + (pr.tile1 > pr.tile_gen ? 1 : 0);
     inf.kernel_launches = idct_launches + (int32_t)b->parts.size() * ((a.prepass_fused ? 1 : 3) + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
@@ -859,7 +864,7 @@ extern "C" int b2j_batch_read_coefs(b2j_batch *b, void *stream, int image, int32
         cudaError_t e = b->ctx->dev_pool.get(bytes, (void **)&b->d_expand, &b->d_expand_cap);
         if (e != cudaSuccess) return fail_cuda(e, "coefficient tap allocation");
     }
-    launch_expand(b->d_coef + (size_t)im.blk_first * 64, b->args.qtabs + (size_t)image * 192, im.blk_count, im.tot_blks, im.ny_blks,
+    launch_expand(b->d_coef + (size_t)im.blk_first * 64, b->args.qtabs + (size_t)image * 192, im.blk_count, im.tot_blks, im.ny_blks, im.nu_blks,
                   b->d_expand, s);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(dst, b->d_expand, bytes, cudaMemcpyDeviceToHost, s));

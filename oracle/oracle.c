@@ -32,8 +32,12 @@
 /* flags for orc_parse */
 #define ORC_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: only (22,11,11) and (11,11,11)   */
 #define ORC_GATE_GRAY 4      /* OR-able extension beyond the reference: one-component (grayscale) frames             */
-#define ORC_GATE_EXTENDED 1  /* also 4:2:2 (21,11,11) and 4:4:0 (12,11,11): the CPU loops of */
-                             /* decoder.cpp:429-495 are generic for 1x1 chroma  */
+#define ORC_GATE_EXTENDED 1  /* every luma sampling h x v (1..4) with 1x1 chroma -- 4:2:2 (21), 4:4:0 (12), 4:1:1  */
+                             /* (41), ... -- which the CPU loops of decoder.cpp:429-495 decode as they are     */
+                             /* (the reference's gate, not its loops, refuses them), and, beyond the  */
+                             /* reference ("only works in ?:1:1 mode", decoder.cpp:455), chroma components with  */
+                             /* several blocks per MCU whose factors divide the luma's (e.g. 22,21,21): the same */
+                             /* pixel replication, sample (x / ratio_h, y / ratio_v) of the component's plane.   */
 
 typedef struct
 {
@@ -255,9 +259,20 @@ static int orc_is_supported(const orc_image *img, int gate)
         if (!img->huff_present[ac | 0x10]) return 0;
     }
     if (img->sampling[1] == 0 && img->sampling[2] == 0) return g_allow_gray && img->sampling[0] == 0x11;
-    if (img->sampling[1] != 0x11 || img->sampling[2] != 0x11) return 0;
-    if (img->sampling[0] == 0x22 || img->sampling[0] == 0x11) return 1;
-    if (gate == ORC_GATE_EXTENDED && (img->sampling[0] == 0x21 || img->sampling[0] == 0x12)) return 1;
+    if (img->sampling[1] == 0x11 && img->sampling[2] == 0x11 && (img->sampling[0] == 0x22 || img->sampling[0] == 0x11)) return 1;
+    if (gate == ORC_GATE_EXTENDED)
+    {
+        const int yh = img->sampling[0] >> 4, yv = img->sampling[0] & 0xF;
+        int tot = yh * yv;
+        if (yh < 1 || yh > 4 || yv < 1 || yv > 4) return 0;
+        for (i = 1; i < 3; i++)
+        {
+            const int h = img->sampling[i] >> 4, v = img->sampling[i] & 0xF;
+            if (h < 1 || v < 1 || yh % h || yv % v) return 0;
+            tot += h * v;
+        }
+        return tot <= 10;   /* ITU T.81 B.2.3: at most 10 blocks per MCU */
+    }
     return 0;
 }
 
@@ -636,11 +651,13 @@ int orc_pixels(const orc_image *img, int32_t *mcu_data, uint8_t *bgra)
 {
     const int yh = img->sampling[0] >> 4, yv = img->sampling[0] & 0xF, yn = yh * yv;
     const int gray = img->blks_per_mcu[1] == 0 && img->blks_per_mcu[2] == 0;
-    const int ruh = gray ? 1 : yh / (img->sampling[1] >> 4), ruv = gray ? 1 : yv / (img->sampling[1] & 0xF);
-    const int rvh = gray ? 1 : yh / (img->sampling[2] >> 4), rvv = gray ? 1 : yv / (img->sampling[2] & 0xF);
+    const int uh = gray ? 1 : img->sampling[1] >> 4, uv = gray ? 1 : img->sampling[1] & 0xF;
+    const int vh = gray ? 1 : img->sampling[2] >> 4, vv = gray ? 1 : img->sampling[2] & 0xF;
+    const int ruh = yh / uh, ruv = yv / uv, rvh = yh / vh, rvv = yv / vv;
+    const int un = gray ? 0 : uh * uv;
     int my, mx, blk, x, y;
     size_t out_blk = 0;
-    if (!gray && (img->blks_per_mcu[1] != 1 || img->blks_per_mcu[2] != 1)) return ORC_E_UNSUPPORTED;
+    if (yh % uh || yv % uv || yh % vh || yv % vv) return ORC_E_UNSUPPORTED;
     for (my = 0; my < img->mcu_count_h; my++)
     {
         for (mx = 0; mx < img->mcu_count_w; mx++)
@@ -660,8 +677,13 @@ int orc_pixels(const orc_image *img, int32_t *mcu_data, uint8_t *bgra)
                     uint8_t *o;
                     if (px >= img->width) break;
                     Y = mat[((y >> 3) * yh + (x >> 3)) * 64 + (((y & 7) << 3) | (x & 7))];
-                    U = gray ? 0 : mat[yn * 64 + ((y / ruv) << 3) + x / ruh];
-                    V = gray ? 0 : mat[(yn + 1) * 64 + ((y / rvv) << 3) + x / rvh];
+                    /* decoder.cpp:478-480 for one chroma block per MCU; with several, the same replication over  */
+                    /* the component's uh x uv blocks (the reference stops with "Unsupported color space")        */
+                    {
+                        const int ux = x / ruh, uy = y / ruv, vx = x / rvh, vy = y / rvv;
+                        U = gray ? 0 : mat[(yn + (uy >> 3) * uh + (ux >> 3)) * 64 + (((uy & 7) << 3) | (ux & 7))];
+                        V = gray ? 0 : mat[(yn + un + (vy >> 3) * vh + (vx >> 3)) * 64 + (((vy & 7) << 3) | (vx & 7))];
+                    }
                     rgb = orc_yuv_to_rgb32(Y, U, V);
                     o = bgra + ((size_t)py * img->width + px) * 4;
                     o[0] = (uint8_t)rgb; o[1] = (uint8_t)(rgb >> 8); o[2] = (uint8_t)(rgb >> 16); o[3] = (uint8_t)(rgb >> 24);

@@ -3,7 +3,7 @@
 tag=${1:-probe}
 o=gpurun_out
 mkdir -p $o
-python -m pytest tests/test_gpu_parity.py -x -q -k "selfsync or other_baseline or randomised or variants or golden or corrupt" > $o/${tag}_pytest.log 2>&1
+python -m pytest tests/test_gpu_parity.py -x -q -k "selfsync or other_baseline or randomised or variants or golden or corrupt or grayscale or dropin" > $o/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> $o/${tag}_pytest.log
 {
   echo "## configs[2]: 64 x 3840x2160 4:4:4 q95";  python tests/prof_run.py 64 10 2

@@ -128,14 +128,18 @@ def _seg(marker, payload):
 
 def build_jpeg(width, height, sampling, blocks, qtabs, restart_interval=0, fill_before_rst=0,
                tables=None, comp_tables=((0, 0), (1, 1), (1, 1)), with_app0=True, trailing=b"", dqt16=False):
-    """sampling: luma (h, v) with 1x1 chroma. blocks: int array [n_blocks, 64] in MCU order and
+    """sampling: luma (h, v) with 1x1 chroma, or ((hy, vy), (hu, vu), (hv, vv)). blocks: int array [n_blocks, 64] in MCU order and
     SCAN (zig-zag) coefficient order, blocks[:,0] = absolute DC. qtabs: two 64-lists (zig-zag order)
     for luma and chroma. tables: dict like STD_TABLES. Returns the file bytes."""
     tables = tables or STD_TABLES
-    h, v = sampling
-    ny = h * v
-    tot = ny + 2
-    mcu_w, mcu_h = 8 * h, 8 * v
+    if isinstance(sampling[0], (tuple, list)):
+        samp = [tuple(x) for x in sampling]          # ((hy, vy), (hu, vu), (hv, vv))
+    else:
+        samp = [tuple(sampling), (1, 1), (1, 1)]
+    h, v = samp[0]
+    nblk = [a * b for a, b in samp]
+    tot = sum(nblk)
+    mcu_w, mcu_h = 8 * max(a for a, _ in samp), 8 * max(b for _, b in samp)
     n_mcu = ((width + mcu_w - 1) // mcu_w) * ((height + mcu_h - 1) // mcu_h)
     blocks = np.asarray(blocks)
     assert blocks.shape == (n_mcu * tot, 64), (blocks.shape, n_mcu * tot)
@@ -149,7 +153,7 @@ def build_jpeg(width, height, sampling, blocks, qtabs, restart_interval=0, fill_
         out += _seg(0xDB, bytes([0]) + bytes(qtabs[0]))
         out += _seg(0xDB, bytes([1]) + bytes(qtabs[1]))
     sof = bytes([8]) + height.to_bytes(2, "big") + width.to_bytes(2, "big") + bytes([3])
-    sof += bytes([1, (h << 4) | v, 0, 2, 0x11, 1, 3, 0x11, 1])
+    sof += bytes([1, (samp[0][0] << 4) | samp[0][1], 0, 2, (samp[1][0] << 4) | samp[1][1], 1, 3, (samp[2][0] << 4) | samp[2][1], 1])
     out += _seg(0xC0, sof)
     for (tc, th), (bits, vals) in sorted(tables.items()):
         out += _seg(0xC4, bytes([(tc << 4) | th]) + bytes(bits) + bytes(vals))
@@ -172,7 +176,7 @@ def build_jpeg(width, height, sampling, blocks, qtabs, restart_interval=0, fill_
             rst += 1
             pred = [0, 0, 0]
         for c in range(3):
-            for _ in range(ny if c == 0 else 1):
+            for _ in range(nblk[c]):
                 dc_codes = codes[(0, comp_tables[c][0])]
                 ac_codes = codes[(1, comp_tables[c][1])]
                 pred[c] = encode_block(bw, blocks[bi], pred[c], dc_codes, ac_codes)

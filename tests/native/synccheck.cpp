@@ -14,7 +14,7 @@
 #include "b2j_internal.h"
 #include "b2j_sync.h"
 
-uint64_t g_b2j_walk_steps[2];
+uint64_t g_b2j_walk_steps[3];
 
 using namespace b2j;
 
@@ -24,6 +24,7 @@ struct HostLut
 {
     const uint16_t *v;
     uint32_t at(uint32_t i) const { return v[i]; }
+    uint32_t at32(uint32_t i) const { return (uint32_t)v[i] | (uint32_t)v[i + 1] << 16; }
     uint32_t hdr(int i) const { return v[i]; }
 };
 
@@ -131,13 +132,13 @@ extern "C" {
 
 // Checks one baseline JPEG without restart markers. Returns 0 when everything agrees, a negative code otherwise.
 // stats[0] sub-sequences, [1] chunks, [2] lanes that walked again in round 1, [3] lanes that missed the checkpoint in
-// round 1, [4] rounds of the slowest chunk, [5] chunks the sweep re-ran, [6] walk-table steps, [7] one-symbol steps,
-// [8] symbols (reference walk), [9] sub-sequences whose walk from the true state disagrees (must be 0).
+// round 1, [4] rounds of the slowest chunk, [5] chunks the sweep re-ran, AC steps of the walks of part 1 (two passes over the
+// stream): [6] whole groups, [7] first symbol of a group, [8] through the decode tables, [9] sub-sequences whose walk from the true state disagrees (must be 0).
 // pre_lanes < 0: kSyncPre. force_sweep: pre-lanes off, so that every chunk border goes through the sweep.
 int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, uint64_t *stats)
 {
     memset(stats, 0, 10 * sizeof(uint64_t));
-    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = 0;
+    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = g_b2j_walk_steps[2] = 0;
     b2j_image_desc d;
     int rc = b2j_parse_header(file, len, gate, &d);
     if (rc != B2J_OK) return -100 + rc;
@@ -204,8 +205,7 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
     }
     if (stats[9]) return -4;
 
-    stats[6] = g_b2j_walk_steps[0]; stats[7] = g_b2j_walk_steps[1];
-    for (uint32_t s = 0; s < n_sub; s++) stats[8] += 0;
+    stats[6] = g_b2j_walk_steps[0]; stats[7] = g_b2j_walk_steps[1]; stats[8] = g_b2j_walk_steps[2];
     // ---- 2. the chunk-wise synchronisation, as the kernels run it
     const uint32_t n_chunks = (n_sub + kSyncLanes - 1) / kSyncLanes;
     stats[1] = n_chunks;
@@ -224,13 +224,14 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
         for (uint32_t round = 1;; round++)
         {
             bool need[kHuffThreads], any = false;
-            for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++) { need[t] = sync_phase_need(ch, *sh, t); any = any || need[t]; }
+            uint2 entry[kHuffThreads];
+            for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++) { need[t] = sync_phase_need(ch, *sh, t, entry[t]); any = any || need[t]; }
             if (!any) break;
             if (round > stats[4]) stats[4] = round;
             for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++)
                 if (need[t])
                 {
-                    const bool met = sync_phase_round(w, ch, *sh, t);
+                    const bool met = sync_phase_round(w, ch, *sh, t, entry[t]);
                     if (round == 1 && !forced) { stats[2]++; if (!met) stats[3]++; }
                 }
             if (round > (uint32_t)kHuffThreads + 1) return false;   // cannot happen: lane k is final after k rounds

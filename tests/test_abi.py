@@ -131,3 +131,36 @@ def test_grayscale_gate_flag(built, oracle):
     # a colour file is unaffected by the flag
     c = synth.synth_jpeg(64, 48, 2, 90, "420", 0)
     assert b2j.parse_header(c, b2j.GATE_REFERENCE | b2j.GATE_GRAY)[0] == 0
+
+
+def test_file_cut_behind_the_sos_header_is_refused(built, fixture_jpeg):
+    """A file that ends right behind the SOS header has no entropy-coded data: the reference gives up on it with
+    "data incomplete" (decoder.cpp:310-314); here the header parser reports B2J_E_DATA and no batch is built."""
+    import ocljpegdecoder_b200 as b2j
+    rc, d = b2j.parse_header(fixture_jpeg, b2j.GATE_REFERENCE)
+    assert rc == 0 and d.scan_size > 0
+    cut = fixture_jpeg[:d.scan_offset]
+    rc, d2 = b2j.parse_header(cut, b2j.GATE_REFERENCE)
+    assert rc == -4                      # B2J_E_DATA
+    rc, _ = b2j.parse_header(fixture_jpeg[:d.scan_offset + 1], b2j.GATE_REFERENCE)
+    assert rc == 0                       # one byte of scan: a batch can be built, the decode flags it
+
+
+def test_huffman_table_ids_above_3_are_refused(built, oracle):
+    """Documented deviation: the reference keeps 16 DC + 16 AC table slots (parser.cpp:176), the C ABI
+    carries ids 0..3 (all that baseline JPEG allows, ITU T.81 B.2.4.2). A DHT with id 4 is a format error here."""
+    import jpegcraft
+    import ocljpegdecoder_b200 as b2j
+    blocks = np.zeros((6, 64), np.int64)
+    tables = dict(jpegcraft.STD_TABLES)
+    tables[(0, 4)] = tables[(0, 0)]
+    data = jpegcraft.build_jpeg(16, 16, (2, 2), blocks, [[1] * 64, [1] * 64], tables=tables)
+    rc, _ = b2j.parse_header(data, b2j.GATE_REFERENCE)
+    assert rc == -2                      # B2J_E_FORMAT
+    # a scan that SELECTS table 4 is refused as well, whatever DHTs are present
+    good = jpegcraft.build_jpeg(16, 16, (2, 2), blocks, [[1] * 64, [1] * 64])
+    k = good.index(b"\xff\xda")
+    bad = bytearray(good)
+    bad[k + 6] = 0x40                    # component 1: Td = 4, Ta = 0
+    rc, _ = b2j.parse_header(bytes(bad), b2j.GATE_REFERENCE)
+    assert rc == -3                      # B2J_E_UNSUPPORTED (the gate: "missing huffman table")

@@ -332,6 +332,39 @@ def test_selfsync_streams_without_restart_markers(decoder, oracle):
     batch.close()
 
 
+def test_selfsync_sweep_repairs_every_chunk_border(decoder, oracle):
+    """B2J_SYNC_PRE=0 switches the pre-lanes off: every chunk but the first of an image starts from a bare guess, so
+    the in-order sweep -- the safety net correctness rests on -- has to re-run nearly every chunk, and the result must
+    not change."""
+    specs = [(1600, 1200, "444", 95), (1024, 768, "420", 75), (2048, 640, "422", 85), (500, 375, "420", 75), (640, 480, "420", 100)]
+    files = [synth.synth_jpeg(w, h, 950 + i, q, ss, 0, optimize=(i % 2 == 1)) for i, (w, h, ss, q) in enumerate(specs)]
+    st0, c0, p0 = _decode(decoder, files)
+    assert not st0.any()
+    os.environ["B2J_SYNC_PRE"] = "0"
+    try:
+        batch = decoder.batch(files)
+    finally:
+        del os.environ["B2J_SYNC_PRE"]
+    batch.upload()
+    batch.decode()
+    assert not batch.status().any()
+    stats = batch.sync_stats()
+    n_chunks = sum(((len(f) + 127) // 128 + 125) // 126 for f in files)
+    print("sync stats without pre-lanes", stats.tolist(), "chunks about", n_chunks)
+    assert stats[7] > n_chunks // 4
+    for i in range(len(files)):
+        assert np.array_equal(batch.coefs(i), c0[i]), i
+        assert np.array_equal(batch.pixels(i), p0[i]), i
+    batch.close()
+    oracle.set_strict(False)
+    try:
+        rc, _, coef, bgra = oracle.decode(files[0])
+    finally:
+        oracle.set_strict(True)
+    assert rc == 0 and np.array_equal(c0[0], coef)
+    _check_pixels(p0[0], bgra)
+
+
 def test_selfsync_corrupt_streams_are_flagged(decoder, oracle):
     good = synth.synth_jpeg(320, 240, 6, 90, "420", 0)
     rc, d = oracle.parse(good)
@@ -555,3 +588,42 @@ def test_grayscale_extension(decoder, oracle):
     for i, b in enumerate(ref):
         assert np.array_equal(batch.pixels(i), np.moveaxis(b[..., 2::-1], 2, 0)), i
     batch.close()
+
+
+def test_dc_category_above_16_is_flagged(decoder, oracle):
+    """Documented deviation (include/b2j.h, DESIGN.md): the reference accepts DC categories up to 25 (decoder.cpp:230);
+    the coefficient plane here is int16, so a DC table symbol above 16 is no codeword to the decoder: the block is
+    flagged B2J_ST_BAD_CODE and the image reported as corrupt instead of decoded with a 17-bit difference."""
+    dc_bits = list(jpegcraft.DC_LUMA_BITS)
+    dc_vals = list(jpegcraft.DC_LUMA_VALS)
+    dc_vals[0] = 17                                  # the 2-bit code now means "category 17"
+    tables = dict(jpegcraft.STD_TABLES)
+    tables[(0, 0)] = (dc_bits, dc_vals)
+    blocks = np.zeros((6, 64), np.int64)             # DC difference 0 everywhere: every luma block starts with that code
+    # category 0 is symbol 0 in the standard table; with the swapped table the writer needs the code of symbol 0 to exist
+    codes = jpegcraft.canonical_codes(dc_bits, dc_vals)
+    assert 0 not in codes and 17 in codes
+    # write the stream by hand: luma DC code for symbol 17 followed by 17 value bits, then EOB; chroma as usual
+    std = {k: jpegcraft.canonical_codes(*v) for k, v in jpegcraft.STD_TABLES.items()}
+    bw = jpegcraft.BitWriter()
+    for b in range(6):
+        if b < 4:
+            code, l = codes[17]
+            bw.put(code, l); bw.put(0x10000, 17)     # +65536
+            code, l = std[(1, 0)][0x00]
+        else:
+            code, l = std[(0, 1)][0]
+            bw.put(code, l)
+            code, l = std[(1, 1)][0x00]
+        bw.put(code, l)
+    bw.flush()
+    shell = jpegcraft.build_jpeg(16, 16, (2, 2), blocks, [[1] * 64, [1] * 64], tables={**tables, (0, 0): (dc_bits, [0] + dc_vals[1:])})
+    k = shell.index(b"\xff\xda")
+    head = bytearray(shell[:k + 14])
+    j = head.index(bytes([0xFF, 0xC4, 0x00, 0x1F, 0x00]))   # the DC luma DHT
+    head[j + 5 + 16] = 17
+    data = bytes(head) + bytes(bw.out) + b"\xff\xd9"
+    good = synth.synth_jpeg(64, 48, 2, 90, "420", 0)
+    st, _, _ = _decode(decoder, [data, good])
+    assert st[1] == 0
+    assert st[0] & 0x01, "DC category 17 must be flagged as B2J_ST_BAD_CODE, status %#x" % st[0]

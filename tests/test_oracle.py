@@ -155,3 +155,74 @@ def test_grayscale_extension_against_pillow(oracle):
             assert np.array_equal(bgra[..., 0], bgra[..., 1]) and np.array_equal(bgra[..., 1], bgra[..., 2]) and not bgra[..., 3].any()
     finally:
         oracle.set_strict(True)
+
+
+GENERIC_LAYOUTS = [((4, 1), (1, 1), (1, 1)), ((1, 4), (1, 1), (1, 1)), ((3, 1), (1, 1), (1, 1)), ((4, 2), (1, 1), (1, 1)),
+                   ((2, 4), (1, 1), (1, 1)), ((1, 3), (1, 1), (1, 1)), ((3, 2), (1, 1), (1, 1))]
+
+
+def _random_blocks(n, seed):
+    rng = np.random.RandomState(seed)
+    blocks = np.zeros((n, 64), np.int64)
+    blocks[:, 0] = np.clip(np.cumsum(rng.randint(-40, 40, n)), -500, 500)
+    for b in range(n):
+        k = rng.randint(0, 12)
+        idx = rng.choice(np.arange(1, 64), k, replace=False)
+        blocks[b, idx] = rng.randint(-30, 30, k)
+    return blocks
+
+
+@pytest.mark.parametrize("samp", GENERIC_LAYOUTS, ids=lambda s: "%d%d" % s[0])
+def test_generic_luma_sampling_oracle_vs_reference(oracle, reference, samp):
+    """Luma h x v beyond the four everyday layouts (4:1:1 = 41, 14, 31, 42, ...) with 1x1 chroma: the reference's gate
+    refuses them, its CPU loops decode them as they are (decoder.cpp:429-495). Oracle (extended gate) against the
+    unmodified reference with the gate skipped: coefficients and pixels bit-exact, with and without restart markers."""
+    import jpegcraft
+    from oracle import GATE_EXTENDED
+    (h, v) = samp[0]
+    w, hgt = 8 * h * 3 - 3, 8 * v * 2 - 1            # 3 x 2 MCUs, ragged right and bottom edges
+    n = 6 * (h * v + 2)
+    for ri in (0, 2):
+        data = jpegcraft.build_jpeg(w, hgt, samp, _random_blocks(n, 7 * h + v + ri), [[2 + (i % 5) for i in range(64)], [3] * 64], restart_interval=ri)
+        assert oracle.parse(data, 0)[0] != 0         # the reference gate refuses it
+        rc, img, coef, bgra = oracle.decode(data, gate=GATE_EXTENDED)
+        assert rc == 0
+        ok, info, rcoef, rbgra, _ = reference.decode(data, skip_gate=True)
+        assert ok
+        assert np.array_equal(coef, rcoef)
+        assert np.array_equal(bgra, rbgra)
+
+
+def test_multi_block_chroma_is_plain_replication(oracle):
+    """Chroma components with several blocks per MCU (22,21,21 and 22,12,12; the reference stops with "Unsupported color
+    space", decoder.cpp:486-490): the oracle's extension is the same pixel replication over the component's blocks.
+    Checked against an independent numpy restatement built from the oracle's own coefficient tap."""
+    import jpegcraft
+    from oracle import GATE_EXTENDED
+    for samp in (((2, 2), (2, 1), (2, 1)), ((2, 2), (1, 2), (1, 2)), ((4, 1), (2, 1), (2, 1)), ((2, 2), (2, 1), (1, 2))):
+        tot = sum(a * b for a, b in samp)
+        mw, mh = 8 * samp[0][0], 8 * samp[0][1]
+        w, hgt = 2 * mw - 5, 2 * mh - 3
+        data = jpegcraft.build_jpeg(w, hgt, samp, _random_blocks(4 * tot, 11), [[1 + (i % 3) for i in range(64)], [2] * 64])
+        rc, img, coef, bgra = oracle.decode(data, gate=GATE_EXTENDED)
+        assert rc == 0, samp
+        # independent restatement: IDCT every block with the oracle's IDCT, assemble planes, replicate, convert
+        planes = []
+        first = 0
+        for (a, b) in samp:
+            pl = np.zeros((2 * 8 * b, 2 * 8 * a), np.int32)
+            for my in range(2):
+                for mx in range(2):
+                    base = (my * 2 + mx) * tot + first
+                    for k in range(a * b):
+                        blk = oracle.idct(coef[base + k]).reshape(8, 8)
+                        pl[my * 8 * b + (k // a) * 8:my * 8 * b + (k // a) * 8 + 8, mx * 8 * a + (k % a) * 8:mx * 8 * a + (k % a) * 8 + 8] = blk
+            planes.append(pl)
+            first += a * b
+        Y = planes[0]
+        U = np.repeat(np.repeat(planes[1], samp[0][1] // samp[1][1], axis=0), samp[0][0] // samp[1][0], axis=1)
+        V = np.repeat(np.repeat(planes[2], samp[0][1] // samp[2][1], axis=0), samp[0][0] // samp[2][0], axis=1)
+        for (x, y) in [(0, 0), (w - 1, hgt - 1), (w // 2, hgt // 2), (mw, mh - 1), (mw - 1, mh)]:
+            want = oracle.yuv_to_rgb32(int(Y[y, x]), int(U[y, x]), int(V[y, x]))
+            got = int(bgra[y, x, 0]) | int(bgra[y, x, 1]) << 8 | int(bgra[y, x, 2]) << 16
+            assert got == want, (samp, x, y)
