@@ -59,7 +59,7 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //        so that position + (bits 5-11) >= 64 exactly when the block is complete behind the set. The group is valid
 //        where position + (bits 5-10) <= 64; a block that fills up without an end-of-block code ends inside a group,
 //        then the first symbol is taken alone.
-//   DC : 16-bit entries, one symbol: bits 0-4 = code length + category, bits 5-9 = category (0..16)
+//   DC : the same 32-bit entry, one symbol in both sets: bits 0-4 = code length + category, bits 5-10 = category (0..16)
 //   0  : take the one-symbol path through the decode tables (code longer than the index, no codeword, category > 16)
 constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table

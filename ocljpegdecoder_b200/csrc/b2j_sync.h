@@ -45,9 +45,9 @@ struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 v = {x, y}; return v; }
 #endif
 
-// host emulation only: counts AC steps: whole groups [0], first symbol of a group [1], through the decode tables [2]
+// host emulation only: counts steps: whole AC groups [0], first symbol of a group [1], through the decode tables [2], DC [3]
 #if defined(B2J_WALK_STATS) && !defined(__CUDACC__)
-extern uint64_t g_b2j_walk_steps[3];
+extern uint64_t g_b2j_walk_steps[4];
 #define B2J_WALK_COUNT(k) (g_b2j_walk_steps[k]++)
 #else
 #define B2J_WALK_COUNT(k) ((void)0)
@@ -136,24 +136,17 @@ struct WalkResult
     int32_t dc0, dc1, dc2;
 };
 
-// Decode tables of one image as the walk sees them. LUT: at(i) reads entry i of the set (u16 units from its start;
-// shared memory on the device), hdr(i) the i-th header word.
-struct WalkTabs
-{
-    uint32_t walk[3];     // per component: DC walk table | AC walk table << 16 (u16 offsets in the set)
-    uint32_t dec[3];      // per component: DC decode table | AC decode table << 16
-};
-
+// Decode tables of one image as the walk sees them. LUT policy: at(i) / at32(i) read the u16 / u32 at u16-offset i of
+// the LUT set (shared memory on the device), hdr(i) the i-th header word, ctab(c) the walk's per-block-index table.
+//
+// ctab(c), c = block index inside the MCU: DC walk table | AC walk table << 15 (u16 offsets in the set, < 32768) |
+// component << 30. Built once per image by walk_ctab_entry(), so that the switch to the next block of the MCU is one
+// lookup instead of a chain of compares and selects.
 template <class LUT>
-B2J_HD WalkTabs walk_tabs(const LUT &lut)
+B2J_HD uint32_t walk_ctab_entry(const LUT &lut, uint32_t c, uint32_t ny, uint32_t nu)
 {
-    WalkTabs t;
-    for (int c = 0; c < 3; c++)
-    {
-        t.walk[c] = lut.hdr(6 + c) | lut.hdr(9 + c) << 16;
-        t.dec[c] = lut.hdr(c) | lut.hdr(3 + c) << 16;
-    }
-    return t;
+    const uint32_t comp = (c >= ny ? 1u : 0u) + (c >= ny + nu ? 1u : 0u);
+    return lut.hdr(6 + (int)comp) | lut.hdr(9 + (int)comp) << 15 | comp << 30;
 }
 
 // One symbol through the two-level decode tables (entry format: b2j_internal.h). Returns the leaf, 0 = no codeword.
@@ -179,12 +172,11 @@ B2J_HD uint32_t lookup_symbol(const LUT &lut, uint32_t tab, uint32_t pk, uint32_
 // alone, and where the walk table has no entry, one symbol goes through the decode tables.
 // From any state -- true or guessed -- the result is a function of that state alone, which is all the
 // synchronisation needs (a guessed walk that reaches a state of the true walk continues exactly like it).
-// Shape: per block one DC step, then AC steps until the block is complete. On the device the lanes of a warp meet again
-// behind every block, so the DC step and the table switch run with all lanes active (they are long, the AC step is short).
-// nu: blocks of component 1 per MCU (component = (c >= ny) + (c >= ny + nu)).
+// Shape: ONE loop, one table lookup per turn whatever the lane is at (DC and AC walk tables share the entry format),
+// because the lanes of a warp sit at unrelated places of their blocks: what only some lanes need -- the DC
+// bookkeeping, the switch to the next block -- is kept short, since every lane pays for it on every turn.
 template <class LUT>
-B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const WalkTabs &tabs, WalkState s, uint32_t limit,
-                              uint32_t tot, uint32_t ny, uint32_t nu)
+B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, WalkState s, uint32_t limit, uint32_t tot)
 {
     WalkResult r;
     r.nblk = 0; r.fs = kSubNone; r.fc = 0; r.dc0 = r.dc1 = r.dc2 = 0;
@@ -196,70 +188,55 @@ B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const W
         br.init(stream, p >> 3);
         br.bitpos += p & 7u;
         const uint32_t lim_group = limit > (uint32_t)kWalkBitsAc ? limit - (uint32_t)(kWalkBitsAc - 1) : 0u;
-        const uint32_t nyu = ny + nu;
+        uint32_t ct = lut.ctab(c);
+        uint32_t tdc = ct & 0x7FFFu, tac = (ct >> 15) & 0x7FFFu, comp = ct >> 30;
         while (p < limit)
         {
-            const uint32_t comp = (c >= ny ? 1u : 0u) + (c >= nyu ? 1u : 0u);
-            const uint32_t tw = comp == 0u ? tabs.walk[0] : (comp == 1u ? tabs.walk[1] : tabs.walk[2]);
-            if (z == 0u)
+            const uint32_t pk = br.peek();
+            const bool dc = z == 0u;
+            const uint32_t e = lut.at32((dc ? tdc : tac) + 2u * (pk >> (dc ? 32u - (uint32_t)kWalkBitsDc : 32u - (uint32_t)kWalkBitsAc)));
+            uint32_t nb, f;
+            if (e != 0u)
             {
-                // ---- DC: starts a block: count it, remember the first one, add its difference to the component's sum
-                const uint32_t pk = br.peek();
-                uint32_t e = lut.at((tw & 0xFFFFu) + (pk >> (32u - (uint32_t)kWalkBitsDc)));
-                uint32_t nb = e & 31u, size = e >> 5;
-                if (e == 0u)
-                {
-                    const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
-                    e = lookup_symbol(lut, td & 0xFFFFu, pk, (uint32_t)kLutBitsDc);
-                    if (e == 0u) { bad = true; break; }
-                    size = (e >> 6) & 31u;
-                    nb = (e & 31u) + size;
-                }
-                const int32_t diff = extend_bits(pk << (nb - size), size);
+                // the whole group where it fits, else its first symbol (a DC entry is its own first symbol)
+                const bool group = p < lim_group && z + ((e >> 5) & 63u) <= 64u;
+                const uint32_t ee = group ? e : e >> 12;
+                nb = ee & 31u;             // bits consumed
+                f = (ee >> 5) & 127u;      // AC: scan positions advanced, >= 64 with the end-of-block flag; DC: category
+                B2J_WALK_COUNT(dc ? 3 : (group ? 0 : 1));
+            }
+            else
+            {
+                B2J_WALK_COUNT(2);
+                const uint32_t e1 = dc ? lookup_symbol(lut, lut.hdr((int)comp), pk, (uint32_t)kLutBitsDc)
+                                       : lookup_symbol(lut, lut.hdr(3 + (int)comp), pk, (uint32_t)kLutBits);
+                if (e1 == 0u) { bad = true; break; }
+                const uint32_t size = (e1 >> 6) & (dc ? 31u : 15u);
+                nb = (e1 & 31u) + size;
+                f = dc ? size : (e1 >> 10) + 1u;   // AC: zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
+            }
+            uint32_t zn = z + f;
+            if (dc)
+            {
+                // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
+                const int32_t diff = extend_bits(pk << (nb - f), f);
                 if (r.nblk == 0u) { r.fs = p; r.fc = c; }
                 r.nblk++;
-                r.dc0 += comp == 0u ? diff : 0;
-                r.dc1 += comp == 1u ? diff : 0;
-                r.dc2 += comp == 2u ? diff : 0;
-                z = 1u;
-                p += nb;
-                br.skip(nb);
+                if (comp == 0u) r.dc0 += diff;
+                if (comp == 1u) r.dc1 += diff;
+                if (comp == 2u) r.dc2 += diff;
+                zn = 1u;
             }
-            // ---- AC steps until the block is complete (or the walk ends)
-            const uint32_t tac = tw >> 16;
-            while (z < 64u && p < limit)
-            {
-                const uint32_t pk = br.peek();
-                const uint32_t e = lut.at32(tac + 2u * (pk >> (32u - (uint32_t)kWalkBitsAc)));
-                uint32_t nb, f;
-                if (e != 0u)
-                {
-                    // the whole group where it fits, else its first symbol
-                    const bool group = p < lim_group && z + ((e >> 5) & 63u) <= 64u;
-                    const uint32_t ee = group ? e : e >> 12;
-                    nb = ee & 31u;             // bits consumed
-                    f = (ee >> 5) & 127u;      // scan positions advanced; >= 64 with the end-of-block flag
-                    B2J_WALK_COUNT(group ? 0 : 1);
-                }
-                else
-                {
-                    B2J_WALK_COUNT(2);
-                    const uint32_t td = comp == 0u ? tabs.dec[0] : (comp == 1u ? tabs.dec[1] : tabs.dec[2]);
-                    const uint32_t e1 = lookup_symbol(lut, td >> 16, pk, (uint32_t)kLutBits);
-                    if (e1 == 0u) { bad = true; break; }
-                    nb = (e1 & 31u) + ((e1 >> 6) & 15u);
-                    f = (e1 >> 10) + 1u;       // zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
-                }
-                z += f;
-                p += nb;
-                br.skip(nb);
-            }
-            if (bad) break;
+            z = zn;
+            p += nb;
+            br.skip(nb);
             if (z >= 64u)
             {
                 // the block is complete: next block of the MCU
                 z = 0u;
                 c = (c + 1u == tot) ? 0u : c + 1u;
+                ct = lut.ctab(c);
+                tdc = ct & 0x7FFFu; tac = (ct >> 15) & 0x7FFFu; comp = ct >> 30;
             }
         }
     }
@@ -274,10 +251,14 @@ B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, const W
 // Per-lane scratch of a chunk (shared memory on the device). Index = lane = thread.
 struct SyncShared
 {
-    SubRec cur[kHuffThreads];       // the lane's record as of the latest round (exit state, totals, first block start)
+    SubRec cur[kHuffThreads];       // the lane's record as of the latest round (exit state, totals, first block start);
+                                    // inside a round, for a lane that goes on to its second half: what its first half found
     SubMid mid[kHuffThreads];       // round 0: state at the middle + the second half's contribution
     uint2 r0_exit[kHuffThreads];    // round 0: exit state (p, cz) -- stands whenever a later walk meets the checkpoint
     uint2 entry_used[kHuffThreads]; // the entry state (p, cz) cur[] was computed from
+    uint32_t nq;                    // lanes in q[]
+    uint8_t q[kHuffThreads];        // this round's lanes that did not meet their checkpoint: their second halves are walked
+                                    // by the first nq threads, so that the few of them fill warps instead of thinning out four
 };
 
 // What a chunk is, for every lane alike.
@@ -286,7 +267,6 @@ struct SyncChunk
     uint32_t first;        // first OUTPUT sub-sequence of the chunk (lane kSyncPre)
     uint32_t n_sub;        // sub-sequences of the image
     uint32_t bits;         // length of the image's clean stream in bits
-    uint32_t tot, ny;      // blocks per MCU, luma blocks per MCU
     uint32_t first_lane;   // first active lane: kSyncPre unless pre-lanes are in use (then max(0, kSyncPre - first))
     bool forced;           // the entry state of lane first_lane is given (true start of the image, or the sweep)
     uint2 forced_entry;    // (p, cz)
@@ -303,58 +283,76 @@ B2J_HD void sync_set(SubRec &d, const WalkResult &r)
     d.p = r.p; d.cz = r.cz; d.nblk = r.nblk; d.dc[0] = r.dc0; d.dc[1] = r.dc1; d.dc[2] = r.dc2; d.fs = r.fs; d.fc = r.fc;
 }
 
-// Walk of sub-sequence `s` from `entry`: first half, checkpoint test (when `check`), second half.
-// Returns true when the walk met the round-0 checkpoint of the lane (then round 0's second half stands).
-template <class W>
-B2J_HD bool sync_walk_lane(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, uint2 entry, bool round0)
+struct SyncBounds { uint32_t md, hi; };
+B2J_HD SyncBounds sync_bounds(const SyncChunk &ch, uint32_t t)
 {
-    const uint32_t s = sync_lane_sub(ch, t);
-    const uint32_t lo = s * (uint32_t)(kSubBytes * 8);
-    const uint32_t hi = lo + (uint32_t)(kSubBytes * 8) < ch.bits ? lo + (uint32_t)(kSubBytes * 8) : ch.bits;
-    const uint32_t md = lo + (uint32_t)(kSubBytes * 4) < hi ? lo + (uint32_t)(kSubBytes * 4) : hi;
+    const uint32_t lo = sync_lane_sub(ch, t) * (uint32_t)(kSubBytes * 8);
+    SyncBounds b;
+    b.hi = lo + (uint32_t)(kSubBytes * 8) < ch.bits ? lo + (uint32_t)(kSubBytes * 8) : ch.bits;
+    b.md = lo + (uint32_t)(kSubBytes * 4) < b.hi ? lo + (uint32_t)(kSubBytes * 4) : b.hi;
+    return b;
+}
+
+// First half of lane t's sub-sequence from `entry`. Round 0: the state reached becomes the lane's checkpoint. Later
+// rounds: if the walk arrives exactly at the checkpoint, round 0's second half stands -- the record is finished and
+// true is returned. Otherwise what the first half found is parked in cur[t] for sync_lane_second().
+template <class W>
+B2J_HD bool sync_lane_first(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, uint2 entry, bool round0)
+{
+    const SyncBounds b = sync_bounds(ch, t);
     const WalkState s0 = {entry.x, entry.y & 0xFFu, entry.y >> 8};
-    const WalkResult ra = w.walk(s0, md);
-    if (!round0)
+    const WalkResult ra = w.walk(s0, b.md);
+    sh.entry_used[t] = entry;
+    SubRec &c = sh.cur[t];
+    if (round0) { sh.mid[t].p = ra.p; sh.mid[t].cz = ra.cz; }
+    else
     {
         const SubMid &m = sh.mid[t];
         if (ra.p == m.p && ra.cz == m.cz)
         {
             // in step at the middle: first half of this walk + second half of round 0; the exit state of round 0 stands
-            SubRec &c = sh.cur[t];
             c.p = sh.r0_exit[t].x; c.cz = sh.r0_exit[t].y;
             c.nblk = ra.nblk + m.nblk;
             c.dc[0] = ra.dc0 + m.dc[0]; c.dc[1] = ra.dc1 + m.dc[1]; c.dc[2] = ra.dc2 + m.dc[2];
             c.fs = ra.fs != kSubNone ? ra.fs : m.fs;
             c.fc = ra.fs != kSubNone ? ra.fc : m.fc;
-            sh.entry_used[t] = entry;
             return true;
         }
     }
-    const WalkState s1 = {ra.p, ra.cz & 0xFFu, ra.cz >> 8};
-    const WalkResult rb = w.walk(s1, hi);
-    WalkResult r = rb;   // exit state of the second half
-    r.nblk = ra.nblk + rb.nblk; r.dc0 = ra.dc0 + rb.dc0; r.dc1 = ra.dc1 + rb.dc1; r.dc2 = ra.dc2 + rb.dc2;
-    if (ra.fs != kSubNone) { r.fs = ra.fs; r.fc = ra.fc; }
-    sync_set(sh.cur[t], r);
-    sh.entry_used[t] = entry;
-    if (round0)
-    {
-        SubMid &m = sh.mid[t];
-        m.p = ra.p; m.cz = ra.cz; m.nblk = rb.nblk; m.dc[0] = rb.dc0; m.dc[1] = rb.dc1; m.dc[2] = rb.dc2; m.fs = rb.fs; m.fc = rb.fc;
-        sh.r0_exit[t] = make_uint2(rb.p, rb.cz);
-    }
+    sync_set(c, ra);
     return false;
 }
 
-// Phase "round 0" of lane t.
+// Second half of lane t's sub-sequence, from where sync_lane_first() stopped.
+template <class W>
+B2J_HD void sync_lane_second(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, bool round0)
+{
+    const SyncBounds b = sync_bounds(ch, t);
+    SubRec &c = sh.cur[t];
+    const WalkState s1 = {c.p, c.cz & 0xFFu, c.cz >> 8};
+    const WalkResult rb = w.walk(s1, b.hi);
+    if (round0)
+    {
+        SubMid &m = sh.mid[t];
+        m.nblk = rb.nblk; m.dc[0] = rb.dc0; m.dc[1] = rb.dc1; m.dc[2] = rb.dc2; m.fs = rb.fs; m.fc = rb.fc;
+        sh.r0_exit[t] = make_uint2(rb.p, rb.cz);
+    }
+    const bool first_seen = c.nblk != 0u;   // fs is only meaningful when a block started
+    c.p = rb.p; c.cz = rb.cz;
+    c.dc[0] += rb.dc0; c.dc[1] += rb.dc1; c.dc[2] += rb.dc2;
+    if (!first_seen) { c.fs = rb.fs; c.fc = rb.fc; }
+    c.nblk += rb.nblk;
+}
+
+// Round 0 of lane t: both halves from the guessed state (its border, block 0, DC expected), or from the given state.
 template <class W>
 B2J_HD void sync_phase_round0(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t)
 {
     if (!sync_lane_active(ch, t)) return;
-    const uint32_t s = sync_lane_sub(ch, t);
     const bool given = ch.forced && t == ch.first_lane;
-    const uint2 entry = given ? ch.forced_entry : make_uint2(s * (uint32_t)(kSubBytes * 8), 0u);
-    sync_walk_lane(w, ch, sh, t, entry, true);
+    const uint2 entry = given ? ch.forced_entry : make_uint2(sync_lane_sub(ch, t) * (uint32_t)(kSubBytes * 8), 0u);
+    sync_lane_first(w, ch, sh, t, entry, true);
+    sync_lane_second(w, ch, sh, t, true);
 }
 
 // Phase "need" of lane t: does the lane have to walk again? Reads the predecessor's exit state BEFORE the round
@@ -365,13 +363,6 @@ B2J_HD bool sync_phase_need(const SyncChunk &ch, const SyncShared &sh, uint32_t 
     if (!sync_lane_active(ch, t) || t == ch.first_lane) return false;
     entry = make_uint2(sh.cur[t - 1].p, sh.cur[t - 1].cz);
     return entry.x != sh.entry_used[t].x || entry.y != sh.entry_used[t].y;
-}
-
-// Phase "round r >= 1" of a lane that needs it. Returns true when the checkpoint was met.
-template <class W>
-B2J_HD bool sync_phase_round(const W &w, const SyncChunk &ch, SyncShared &sh, uint32_t t, uint2 entry)
-{
-    return sync_walk_lane(w, ch, sh, t, entry, false);
 }
 
 } // namespace b2j

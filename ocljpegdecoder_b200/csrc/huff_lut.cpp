@@ -115,18 +115,22 @@ bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
         }
         return nullptr;
     };
+    // 32-bit entries, stored as two u16 each (little endian): set 0 = the whole group, set 1 = its first symbol
+    out.assign((size_t)2 << K, 0);
     if (is_dc)
     {
-        out.assign((size_t)1 << K, 0);
+        // one symbol, both sets alike: bits consumed = code length + category, the category in the position field
         for (uint32_t w = 0; w < (1u << K); w++)
         {
             const Code *c = match(w, 0);
-            if (c && c->sym <= 16) out[w] = (uint16_t)((c->len + c->sym) | (c->sym << 5));
+            if (!c || c->sym > 16) continue;
+            const uint32_t set = (uint32_t)(c->len + c->sym) | (uint32_t)c->sym << 5;
+            const uint32_t v = set | set << 12;
+            out[2 * w] = (uint16_t)v;
+            out[2 * w + 1] = (uint16_t)(v >> 16);
         }
         return true;
     }
-    // AC: 32-bit entries, stored as two u16 each (little endian): set 0 = the whole group, set 1 = its first symbol
-    out.assign((size_t)2 << K, 0);
     for (uint32_t w = 0; w < (1u << K); w++)
     {
         int pos = 0, zadv = 0, nsym = 0, nbits = 0, eob = 0;

@@ -1124,9 +1124,11 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 struct DevLut
 {
     uint32_t sm;            // shared-window byte address of the set
-    const uint16_t *s;      // the same, as a pointer (header reads outside the loops)
+    uint32_t ct;            // shared-window byte address of the per-block-index table (walk_ctab_entry)
+    const uint16_t *s;      // the set as a pointer (header reads outside the loops)
     __device__ __forceinline__ uint32_t at(uint32_t i) const { return lds_u16(sm + (i << 1)); }
     __device__ __forceinline__ uint32_t at32(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm + (i << 1))); return v; }
+    __device__ __forceinline__ uint32_t ctab(uint32_t c) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ct + (c << 2))); return v; }
     __device__ __forceinline__ uint32_t hdr(int i) const { return s[i]; }
 };
 
@@ -1134,16 +1136,17 @@ struct DevWalk
 {
     StreamWords stream;
     DevLut lut;
-    WalkTabs tabs;
-    uint32_t tot, ny, nu;
-    __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_lut, const uint16_t *s_lut, const ImgDev &im)
+    uint32_t tot;
+    // s_ctab: 16 words of shared memory, filled here by the first `tot` threads (the caller synchronises afterwards)
+    __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_lut, const uint16_t *s_lut, uint32_t *s_ctab, const ImgDev &im)
     {
         stream.w = reinterpret_cast<const uint32_t *>(clean_img);
         lut.sm = sm_lut; lut.s = s_lut;
-        tabs = walk_tabs(lut);
-        tot = im.tot_blks; ny = im.ny_blks; nu = im.nu_blks;
+        asm volatile("mov.u32 %0, %1;" : "=r"(lut.ct) : "r"(smem_addr(s_ctab)));   // opaque: otherwise the window base is re-derived inside the loop
+        tot = im.tot_blks;
+        if (threadIdx.x < tot && threadIdx.x < 16u) s_ctab[threadIdx.x] = walk_ctab_entry(lut, threadIdx.x, im.ny_blks, im.nu_blks);
     }
-    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, tabs, s, limit, tot, ny, nu); }
+    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit, tot); }
 };
 
 // ---- chunk-wise synchronisation (b2j_sync.h): all rounds of a chunk of kSyncLanes sub-sequences inside one CTA.
@@ -1160,13 +1163,21 @@ __device__ __forceinline__ void sync_run_chunk(const DevWalk &wk, SyncShared &sh
     __syncthreads();
     for (uint32_t round = 1; round <= (uint32_t)kHuffThreads + 1u; round++)   // lane k of a chunk is final after k rounds
     {
+        if (tid == 0) sh.nq = 0u;
         uint2 entry;
         const bool need = sync_phase_need(ch, sh, tid, entry);
         if (!__syncthreads_or(need)) break;   // also orders the reads of cur[] above before the writes below
         bool met = true;
-        if (need) met = sync_phase_round(wk, ch, sh, tid, entry);
+        if (need)
+        {
+            met = sync_lane_first(wk, ch, sh, tid, entry, false);
+            if (!met) sh.q[atomicAdd(&sh.nq, 1u)] = (uint8_t)tid;
+        }
         const int missed = __syncthreads_count(need && !met);
+        // the lanes that did not meet their checkpoint, packed into the first warps
+        if (tid < (uint32_t)missed) sync_lane_second(wk, ch, sh, sh.q[tid], false);
         if (tid == 0 && missed && stats) atomicAdd(&stats[round < 6u ? round : 6u], (uint32_t)missed);
+        __syncthreads();
     }
     // ---- output: the records of the chunk's own lanes, its totals, its entry and exit state
     const bool out = tid >= (uint32_t)kSyncPre && sync_lane_active(ch, tid);
@@ -1218,6 +1229,7 @@ k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_wtot[kHuffThreads / 32];
+    __shared__ uint32_t s_ctab[16];
     SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -1235,9 +1247,10 @@ k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint32_t sm_lut;
     asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
     DevWalk wk;
-    wk.init(clean + im.raw_off, sm_lut, s_lut, im);
+    wk.init(clean + im.raw_off, sm_lut, s_lut, s_ctab, im);
+    __syncthreads();
     SyncChunk ch;
-    ch.first = cta.seg_first; ch.n_sub = n_sub; ch.bits = bits; ch.tot = im.tot_blks; ch.ny = im.ny_blks;
+    ch.first = cta.seg_first; ch.n_sub = n_sub; ch.bits = bits;
     const bool pre = use_pre != 0u && cta.seg_first != 0u;
     ch.first_lane = pre ? (cta.seg_first >= (uint32_t)kSyncPre ? 0u : (uint32_t)kSyncPre - cta.seg_first) : (uint32_t)kSyncPre;
     ch.forced = cta.seg_first == 0u;          // the first chunk of an image starts from the true state
@@ -1255,6 +1268,7 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_wtot[kHuffThreads / 32];
+    __shared__ uint32_t s_ctab[16];
     __shared__ uint32_t s_min;
     SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
@@ -1299,10 +1313,11 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
         uint32_t sm_lut;
         asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
         DevWalk wk;
-        wk.init(clean + im.raw_off, sm_lut, s_lut, im);
+        wk.init(clean + im.raw_off, sm_lut, s_lut, s_ctab, im);
+        __syncthreads();
         const uint4 prev = __ldcg(state + found - 1u);
         SyncChunk ch;
-        ch.first = found * (uint32_t)kSyncLanes; ch.n_sub = n_sub; ch.bits = bits; ch.tot = im.tot_blks; ch.ny = im.ny_blks;
+        ch.first = found * (uint32_t)kSyncLanes; ch.n_sub = n_sub; ch.bits = bits;
         ch.first_lane = (uint32_t)kSyncPre;
         ch.forced = true;
         ch.forced_entry = make_uint2(prev.z, prev.w);

@@ -14,7 +14,7 @@
 #include "b2j_internal.h"
 #include "b2j_sync.h"
 
-uint64_t g_b2j_walk_steps[3];
+uint64_t g_b2j_walk_steps[4];
 
 using namespace b2j;
 
@@ -23,18 +23,20 @@ namespace {
 struct HostLut
 {
     const uint16_t *v;
+    uint32_t ct[16];
     uint32_t at(uint32_t i) const { return v[i]; }
     uint32_t at32(uint32_t i) const { return (uint32_t)v[i] | (uint32_t)v[i + 1] << 16; }
     uint32_t hdr(int i) const { return v[i]; }
+    uint32_t ctab(uint32_t c) const { return ct[c]; }
 };
 
 struct HostWalk
 {
     StreamWords stream;
     HostLut lut;
-    WalkTabs tabs;
     uint32_t tot, ny, nu;
-    WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, tabs, s, limit, tot, ny, nu); }
+    void init() { for (uint32_t c = 0; c < tot && c < 16; c++) lut.ct[c] = walk_ctab_entry(lut, c, ny, nu); }
+    WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit, tot); }
 };
 
 // ---- the independent check: canonical codes matched bit by bit, one symbol per step ----------------------------
@@ -138,7 +140,7 @@ extern "C" {
 int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, uint64_t *stats)
 {
     memset(stats, 0, 10 * sizeof(uint64_t));
-    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = g_b2j_walk_steps[2] = 0;
+    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = g_b2j_walk_steps[2] = g_b2j_walk_steps[3] = 0;
     b2j_image_desc d;
     int rc = b2j_parse_header(file, len, gate, &d);
     if (rc != B2J_OK) return -100 + rc;
@@ -174,8 +176,8 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
     HostWalk w;
     w.stream.w = reinterpret_cast<const uint32_t *>(clean.data());
     w.lut.v = set.data();
-    w.tabs = walk_tabs(w.lut);
     w.tot = ref.tot; w.ny = ref.ny; w.nu = ref.nu ? ref.nu : 1u;
+    w.init();
 
     // ---- 1. the truth, sequentially; and the walk from the true state of every sub-sequence, whole and in halves
     std::vector<WalkResult> truth(n_sub);
@@ -214,7 +216,7 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
     SyncShared *sh = new SyncShared;
     auto run_chunk = [&](uint32_t k, bool forced, uint2 entry) {
         SyncChunk ch;
-        ch.first = k * kSyncLanes; ch.n_sub = n_sub; ch.bits = bits; ch.tot = w.tot; ch.ny = w.ny;
+        ch.first = k * kSyncLanes; ch.n_sub = n_sub; ch.bits = bits;
         const bool pre = !forced && !force_sweep && k > 0;
         ch.first_lane = pre ? (ch.first >= (uint32_t)kSyncPre ? 0u : kSyncPre - ch.first) : (uint32_t)kSyncPre;
         ch.forced = forced || k == 0;
@@ -223,17 +225,21 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
         for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++) sync_phase_round0(w, ch, *sh, t);
         for (uint32_t round = 1;; round++)
         {
+            // the phases of a round, each for every lane before the next one starts (barriers on the device)
             bool need[kHuffThreads], any = false;
-            uint2 entry[kHuffThreads];
-            for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++) { need[t] = sync_phase_need(ch, *sh, t, entry[t]); any = any || need[t]; }
+            uint2 ent[kHuffThreads];
+            sh->nq = 0;
+            for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++) { need[t] = sync_phase_need(ch, *sh, t, ent[t]); any = any || need[t]; }
             if (!any) break;
             if (round > stats[4]) stats[4] = round;
             for (uint32_t t = 0; t < (uint32_t)kHuffThreads; t++)
                 if (need[t])
                 {
-                    const bool met = sync_phase_round(w, ch, *sh, t, entry[t]);
+                    const bool met = sync_lane_first(w, ch, *sh, t, ent[t], false);
+                    if (!met) sh->q[sh->nq++] = (uint8_t)t;
                     if (round == 1 && !forced) { stats[2]++; if (!met) stats[3]++; }
                 }
+            for (uint32_t i = 0; i < sh->nq; i++) sync_lane_second(w, ch, *sh, sh->q[i], false);
             if (round > (uint32_t)kHuffThreads + 1) return false;   // cannot happen: lane k is final after k rounds
         }
         uint32_t last = kSyncPre;
