@@ -502,7 +502,20 @@ def main():
         assert not st2.any()
         e2e = {"value": round(pix_job / e2e_s / 1e6, 1), "unit": "MPix/s", "h2d_bytes_per_step": int(allsum(float(info.h2d_bytes))),
                "d2h_bytes_per_step": int(allsum(float(info.pixel_bytes))), "ms_per_step": round(e2e_s * 1e3, 3),
-               "api": "b2j_decode_host: parse + stage + H2D + decode + D2H into pinned host buffers"}
+               "api": "b2j_decode_host: parse + stage (host threads) + H2D + decode + D2H into pinned host buffers, the reference's BGRA"}
+        # the same call with RGB24 output (b2j_decode_host_ex): 25 % fewer bytes over PCIe, which is what bounds e2e
+        outs3 = [flat[i * img_bytes:i * img_bytes + img_bytes // 4 * 3].view(c["height"], c["width"], 3).numpy() for i in range(len(files))]
+        dec.decode_host_ex(files, outs=outs3, out_format=b2j.OUT_RGB24)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _, st3 = dec.decode_host_ex(files, outs=outs3, out_format=b2j.OUT_RGB24)
+        barrier()
+        e2e3_s = allmax((time.perf_counter() - t0) / args.e2e_steps)
+        assert not st3.any()
+        e2e["rgb24"] = {"value": round(pix_job / e2e3_s / 1e6, 1), "unit": "MPix/s", "ms_per_step": round(e2e3_s * 1e3, 3),
+                        "d2h_bytes_per_step": int(allsum(float(info.pixel_bytes))) // 4 * 3,
+                        "api": "b2j_decode_host_ex(out_format = B2J_OUT_RGB24): same pixels, three bytes each"}
 
     sampler.stop_flag.set()
     sampler.join(timeout=2)

@@ -29,8 +29,14 @@
  *   b2j_batch_read_coefs    idct.h:15           clidct_retrieve_data_from_device(): int32[blk][64],
  *                                               natural order, dequantised == JPG_DATA::mcu_data
  *                                               after decode_huffman_data() (jpeg.h:74)
- *   b2j_decode_host         parser.cpp:376-397  the whole per-file sequence, batched, host buffers
- *                                               in and out
+ *   b2j_decode_host(_ex)    parser.cpp:376-397  the whole per-file sequence, batched, host buffers
+ *                                               in and out; _ex: output layout, host threads for parsing/staging
+ *   b2j_decode_host_multi   main.cpp:17-37      one call over several GPUs: images are sharded by compressed bytes,
+ *                                               one host thread and one context per GPU, no exchange between them
+ *   b2j_read_files          decoder.cpp:94-101  the 2 KiB fread() loop (and main.cpp's fopen): whole files read with
+ *                                               several threads into one pinned arena
+ *   b2j_host_alloc/free     oclDCT8x8.cpp:112-165 the host side of clidct_allocate_memory(): pinned buffers, so that
+ *                                               the device<->host copies run at PCIe speed
  *
  * The C++ shim that keeps the reference's own four decoder.h signatures on top of this ABI is
  * ocljpegdecoder_b200/csrc/refshim/; INTEGRATION.md shows the binding.
@@ -45,7 +51,7 @@
 extern "C" {
 #endif
 
-#define B2J_ABI_VERSION 2
+#define B2J_ABI_VERSION 3
 
 /* ---- return codes (0 = success, like the reference's `true`) ---- */
 #define B2J_OK 0
@@ -214,6 +220,38 @@ int b2j_batch_read_coefs(b2j_batch *batch, void *stream, int image, int32_t *dst
  * header is rejected get status[i] = the negative B2J_E_* code and are skipped. */
 int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, int gate,
                     uint8_t *const *out_bgra, int32_t *status);
+
+/* Options of b2j_decode_host_ex() / b2j_decode_host_multi(); zero-initialise, then set what differs. */
+typedef struct b2j_host_opts
+{
+    int32_t gate;        /* B2J_GATE_* and the OR-able parse flags                                                */
+    int32_t out_format;  /* B2J_OUT_*: BGRA (w*h*4 bytes per image), RGB24 or planar RGB (w*h*3 bytes)             */
+    int32_t n_threads;   /* host threads that parse headers and stage scans into pinned memory; 0 = as many as
+                          * the machine offers, at most 8                                                        */
+    int32_t group;       /* images per pipeline group (0 = 32): a group is uploaded, decoded and read back as one */
+    int32_t reserved[4]; /* 0                                                                                     */
+} b2j_host_opts;
+
+/* b2j_decode_host() with options: the pixels arrive in opts->out_format (RGB24 moves 25 % fewer bytes over PCIe,
+ * which is what bounds this call), headers are parsed and scans staged by opts->n_threads host threads while the
+ * calling thread only enqueues uploads, decodes and downloads. out[i]: w*h*4 or w*h*3 bytes. */
+int b2j_decode_host_ex(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, const b2j_host_opts *opts,
+                       uint8_t *const *out, int32_t *status);
+
+/* The same over several devices: ctxs[k] = a context on the k-th device to use (b2j_create(device)); image i goes to
+ * exactly one of them (contiguous index ranges of about equal compressed size). One host thread per context runs
+ * b2j_decode_host_ex() on its range; nothing is exchanged between devices. Returns the first failure, if any. */
+int b2j_decode_host_multi(b2j_ctx *const *ctxs, int n_ctx, int n, const uint8_t *const *files, const size_t *lens,
+                          const b2j_host_opts *opts, uint8_t *const *out, int32_t *status);
+
+/* Pinned (page-locked, all devices) host memory for inputs and outputs of the calls above. */
+int b2j_host_alloc(void **out, size_t bytes);
+void b2j_host_free(void *p);
+
+/* Reads n whole files with n_threads (0 = auto) into one pinned arena: files[i] / lens[i] are filled in, *arena is
+ * what to pass to b2j_host_free() afterwards. A file that cannot be read gets files[i] = NULL, lens[i] = 0 and the
+ * call returns B2J_E_ARG after reading the others. */
+int b2j_read_files(int n, const char *const *paths, int n_threads, void **arena, const uint8_t **files, size_t *lens);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "b2j_create", "b2j_destroy", "b2j_batch_create", "b2j_batch_destroy", "b2j_batch_get_info",
     "b2j_batch_upload", "b2j_batch_set_output_format", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status", "b2j_batch_sync_stats",
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
-    "b2j_batch_read_coefs", "b2j_decode_host",
+    "b2j_batch_read_coefs", "b2j_decode_host", "b2j_decode_host_ex", "b2j_decode_host_multi", "b2j_host_alloc", "b2j_host_free",
+    "b2j_read_files",
 ]
 
 
@@ -57,6 +58,12 @@ class BatchInfo(ctypes.Structure):
         ("coef_plane_bytes", ctypes.c_int64), ("pixel_bytes", ctypes.c_int64), ("algorithmic_bytes", ctypes.c_int64),
         ("device_bytes", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
     ]
+
+
+class HostOpts(ctypes.Structure):
+    """b2j_host_opts"""
+    _fields_ = [("gate", ctypes.c_int32), ("out_format", ctypes.c_int32), ("n_threads", ctypes.c_int32), ("group", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 4)]
 
 
 class StageTimes(ctypes.Structure):
@@ -111,6 +118,14 @@ def load_library():
     L.b2j_batch_read_coefs.argtypes = [vp, vp, ci, vp]
     L.b2j_decode_host.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t), ci,
                                   ctypes.POINTER(vp), vp]
+    L.b2j_decode_host_ex.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(HostOpts),
+                                     ctypes.POINTER(vp), vp]
+    L.b2j_decode_host_multi.argtypes = [ctypes.POINTER(vp), ci, ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t),
+                                        ctypes.POINTER(HostOpts), ctypes.POINTER(vp), vp]
+    L.b2j_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.b2j_host_free.argtypes = [vp]
+    L.b2j_host_free.restype = None
+    L.b2j_read_files.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     _LIB = L
     return L
 
@@ -127,6 +142,80 @@ def parse_header(data, gate=GATE_EXTENDED):
     d = ImageDesc()
     rc = L.b2j_parse_header(data, len(data), gate, ctypes.byref(d))
     return rc, d
+
+
+def _out_shape(d, fmt):
+    return (d.height, d.width, 4) if fmt == OUT_BGRA else ((d.height, d.width, 3) if fmt == OUT_RGB24 else (3, d.height, d.width))
+
+
+def _host_call_args(files, outs, gate, fmt):
+    """Argument arrays of the b2j_decode_host* calls; allocates the outputs when none are given."""
+    n = len(files)
+    if outs is None:
+        outs = []
+        for f in files:
+            rc, d = parse_header(f, gate)
+            outs.append(np.zeros(_out_shape(d, fmt), np.uint8) if rc == 0 else np.zeros((0, 0, 4), np.uint8))
+    ptrs = [f if isinstance(f, int) else ctypes.cast(ctypes.c_char_p(f), ctypes.c_void_p).value for f in files]
+    fp = ctypes.cast((ctypes.c_void_p * n)(*ptrs), ctypes.POINTER(ctypes.c_char_p))
+    return outs, fp, (ctypes.c_void_p * n)(*[o if isinstance(o, int) else o.ctypes.data for o in outs])
+
+
+class PinnedBuffer:
+    """b2j_host_alloc / b2j_host_free: page-locked host memory, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        self.lib = load_library()
+        self._p = ctypes.c_void_p()
+        _check(self.lib.b2j_host_alloc(ctypes.byref(self._p), nbytes), "b2j_host_alloc")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(ctypes.cast(self._p, ctypes.POINTER(ctypes.c_uint8)), shape=(max(nbytes, 1),))[:nbytes]
+
+    @property
+    def address(self):
+        return self._p.value
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self.lib.b2j_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_files(paths, n_threads=0):
+    """b2j_read_files: whole files into one pinned arena. Returns (arena address -- pass to host_free() --, [address], [length])."""
+    L = load_library()
+    n = len(paths)
+    pp = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    arena = ctypes.c_void_p()
+    fl = (ctypes.c_void_p * n)()
+    ln = (ctypes.c_size_t * n)()
+    rc = L.b2j_read_files(n, pp, n_threads, ctypes.byref(arena), fl, ln)
+    return rc, arena.value, [fl[i] for i in range(n)], [ln[i] for i in range(n)]
+
+
+def host_free(address):
+    load_library().b2j_host_free(ctypes.c_void_p(address))
+
+
+def decode_host_multi(decoders, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0):
+    """b2j_decode_host_multi over the given Decoder objects (one per GPU). files: bytes objects or addresses (then `lens`)."""
+    L = load_library()
+    n = len(files)
+    lens = lens if lens is not None else [len(f) for f in files]
+    outs, fp, op = _host_call_args(files, outs, gate, out_format)
+    ln = (ctypes.c_size_t * n)(*lens)
+    opts = HostOpts(gate=gate, out_format=out_format, n_threads=n_threads, group=group)
+    cx = (ctypes.c_void_p * len(decoders))(*[d._h.value for d in decoders])
+    status = np.zeros(n, np.int32)
+    _check(L.b2j_decode_host_multi(cx, len(decoders), n, fp, ln, ctypes.byref(opts), op, status.ctypes.data), "b2j_decode_host_multi")
+    return outs, status
 
 
 class Decoder:
@@ -170,6 +259,19 @@ class Decoder:
         op = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
         status = np.zeros(n, np.int32)
         _check(self.lib.b2j_decode_host(self._h, n, fp, ln, gate, op, status.ctypes.data), "b2j_decode_host")
+        return outs, status
+
+
+    def decode_host_ex(self, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0):
+        """b2j_decode_host_ex: like decode_host with an output layout and host threads. files: bytes objects or addresses
+        (then `lens`); outs: numpy arrays or addresses."""
+        n = len(files)
+        lens = lens if lens is not None else [len(f) for f in files]
+        outs, fp, op = _host_call_args(files, outs, gate, out_format)
+        ln = (ctypes.c_size_t * n)(*lens)
+        opts = HostOpts(gate=gate, out_format=out_format, n_threads=n_threads, group=group)
+        status = np.zeros(n, np.int32)
+        _check(self.lib.b2j_decode_host_ex(self._h, n, fp, ln, ctypes.byref(opts), op, status.ctypes.data), "b2j_decode_host_ex")
         return outs, status
 
 

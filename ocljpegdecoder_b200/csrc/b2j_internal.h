@@ -17,7 +17,10 @@ constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of r
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
 constexpr int kSubBytes = 128;           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
 constexpr int kSyncRounds = 6;           // parallel synchronisation rounds before the sequential sweep
-constexpr int kSyncPre = 2;              // chunk-wise synchronisation (b2j_sync.h): sub-sequences walked in front of a chunk
+#ifndef B2J_SYNC_PRE_LANES
+#define B2J_SYNC_PRE_LANES 2
+#endif
+constexpr int kSyncPre = B2J_SYNC_PRE_LANES;   // chunk-wise synchronisation (b2j_sync.h): sub-sequences walked in front of a chunk
 constexpr int kSyncLanes = kHuffThreads - kSyncPre;   // output sub-sequences per chunk
 #ifndef B2J_LUT_BITS
 #define B2J_LUT_BITS 10
@@ -30,11 +33,10 @@ constexpr int kLutHeader = 16;           // u16 words of header in front of a LU
                                          //   [12]   length of the decode part of the set (header + decode tables), a multiple of 8
 constexpr int kLutMaxDecode = 12288;     // u16 entries of the decode part of a LUT set (24 KB of shared memory)
 constexpr int kLutMaxEntries = 32768;    // u16 entries of a whole LUT set, walk tables included (64 KB)
-#ifndef B2J_WALK_BITS_AC
-#define B2J_WALK_BITS_AC 11
+#ifndef B2J_WALK_BITS
+#define B2J_WALK_BITS 10
 #endif
-constexpr int kWalkBitsAc = B2J_WALK_BITS_AC;   // index width of the AC walk tables (several symbols per lookup)
-constexpr int kWalkBitsDc = 9;           // index width of the DC walk tables
+constexpr int kWalkBits = B2J_WALK_BITS; // index width of the walk tables, DC and AC alike (several AC symbols per lookup)
 constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
 constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
@@ -49,18 +51,25 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //   escape  : bits 0-5  = extra index bits nb (1..16 - primary width, i.e. < 32: bit 5 clear), bits 6-15 = sub-table
 //             offset relative to the end of the primary table, in units of kLutSubAlign entries
 //   invalid : 0 (no codeword has this prefix)
-// Walk tables, used by the walks of the self-synchronising path only (they need no coefficient values):
-//   AC : 32-bit entries. The symbols whose CODES lie completely inside the next kWalkBitsAc bits, up to and including
-//        an end-of-block, form a group. Two 12-bit field sets, the group (bits 0-11) and its first symbol (bits 12-23):
+// Walk tables, used by the walks of the self-synchronising path only (they need no coefficient values): 32-bit
+// entries indexed by the next kWalkBits bits, two 16-bit halves of one layout:
 //          bits 0-4  bits consumed (codes + value bits, <= 31)
-//          bits 5-10 scan positions needed: sum of run + 1, plus 1 when the set ends with the end-of-block symbol
-//                    (the block must not be complete in front of it); <= 63
-//          bit  11   the set ends with the end-of-block symbol
-//        so that position + (bits 5-11) >= 64 exactly when the block is complete behind the set. The group is valid
-//        where position + (bits 5-10) <= 64; a block that fills up without an end-of-block code ends inside a group,
-//        then the first symbol is taken alone.
-//   DC : the same 32-bit entry, one symbol in both sets: bits 0-4 = code length + category, bits 5-10 = category (0..16)
-//   0  : take the one-symbol path through the decode tables (code longer than the index, no codeword, category > 16)
+//          bit  7    the set ends with the end-of-block symbol
+//          bits 8-15 scan positions needed: sum of run + 1, plus 1 for a closing end-of-block symbol (the block must
+//                    not be complete in front of it); <= 64; 0xFF = no entry
+//   AC : the symbols whose CODES lie completely inside the index, up to and including an end-of-block, form a group.
+//        Low half = the group, high half = its first symbol alone. The group is taken where position + (bits 8-15)
+//        <= 64 (a block that fills up without an end-of-block code ends inside a group: then the first symbol is
+//        taken alone); the block is complete behind a set when its bit 7 is set or the position reaches 64.
+//   DC : low half = the symbol where code + value bits fit into the index (bits consumed = code length + category,
+//        positions = 1), high half = the DC difference itself (int16).
+//   bits 8-15 of the low half above 64 mark the special entries:
+//   0xFE (AC) : escape -- the code is longer than the index: bits 0-4 = further index bits nb, bits 16-31 = position of
+//               a sub-table of 1 << nb one-symbol entries (both halves alike), counted in entries from the table start
+//   0xFD (DC) : the value bits reach past the index: bits 0-4 = code length, bits 16-20 = category
+//   0xFF      : no entry (kWalkNoEntry): one symbol through the decode tables (DC code longer than the index) or no codeword
+constexpr uint32_t kWalkNoEntry = 0xFF00FF00u;
+constexpr uint32_t kWalkEscape = 0xFEu, kWalkDcWide = 0xFDu;
 constexpr uint32_t kRunEob = 63;
 constexpr uint32_t kLutSubAlign = 8;     // sub-tables start on multiples of 8 entries behind the primary table
 
@@ -133,7 +142,7 @@ struct TileDev
 // (code space overflow) or needs more than `max_entries` entries.
 bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out, size_t max_entries);
 
-// Canonical Huffman table -> walk table (1 << kWalkBitsDc or 1 << kWalkBitsAc entries, format above).
+// Canonical Huffman table -> walk table (1 << kWalkBits 32-bit entries as pairs of u16, format above).
 bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out);
 
 // LUT set for one image: header (offsets of the DC/AC table of each component) + tables.

@@ -45,9 +45,9 @@ struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 v = {x, y}; return v; }
 #endif
 
-// host emulation only: counts steps: whole AC groups [0], first symbol of a group [1], through the decode tables [2], DC [3]
+// host emulation only: counts steps: whole AC groups [0], first symbol of a group [1], through the decode tables [2], DC [3], escapes / wide DC [4]
 #if defined(B2J_WALK_STATS) && !defined(__CUDACC__)
-extern uint64_t g_b2j_walk_steps[4];
+extern uint64_t g_b2j_walk_steps[5];
 #define B2J_WALK_COUNT(k) (g_b2j_walk_steps[k]++)
 #else
 #define B2J_WALK_COUNT(k) ((void)0)
@@ -72,6 +72,15 @@ B2J_HD uint32_t bswap32(uint32_t v)
     return __byte_perm(v, 0, 0x0123);
 #else
     return __builtin_bswap32(v);
+#endif
+}
+// bits 8-15 of a word
+B2J_HD uint32_t byte1(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0, 0x4441);
+#else
+    return (v >> 8) & 0xFFu;
 #endif
 }
 // Value bits -> signed coefficient (JPEG EXTEND, decoder.cpp:72-82). v: the bits left-aligned, size = their number
@@ -136,17 +145,35 @@ struct WalkResult
     int32_t dc0, dc1, dc2;
 };
 
-// Decode tables of one image as the walk sees them. LUT policy: at(i) / at32(i) read the u16 / u32 at u16-offset i of
-// the LUT set (shared memory on the device), hdr(i) the i-th header word, ctab(c) the walk's per-block-index table.
-//
-// ctab(c), c = block index inside the MCU: DC walk table | AC walk table << 15 (u16 offsets in the set, < 32768) |
-// component << 30. Built once per image by walk_ctab_entry(), so that the switch to the next block of the MCU is one
-// lookup instead of a chain of compares and selects.
+// What the walk needs to know about block c of the MCU (c = block index inside the MCU), one lookup at every block
+// switch instead of a chain of compares and selects. Built once per image by walk_ctab_entry().
+struct WalkCtab
+{
+    uint32_t tdc, tac;     // table handles (LUT::tab) of the block's DC and AC walk tables
+    uint32_t next;         // block index of the next block of the MCU (wraps to 0)
+    uint32_t comp;         // component of the block (the one-symbol path picks its decode tables by it)
+    uint32_t m1, m2;       // all ones when the block belongs to component 1 / 2 (DC sums without compares)
+    uint32_t pad0, pad1;
+};
+
+// Decode tables of one image as the walk sees them. LUT policy:
+//   tab(o)     handle of the walk table at u16-offset o of the LUT set (device: its shared-window byte address)
+//   ld(h, i)   32-bit entry i of the walk table with handle h
+//   ctab(c)    the WalkCtab of block c
+//   at(i)      the u16 at u16-offset i of the set, hdr(i) the i-th header word (one-symbol path through the decode tables)
 template <class LUT>
-B2J_HD uint32_t walk_ctab_entry(const LUT &lut, uint32_t c, uint32_t ny, uint32_t nu)
+B2J_HD WalkCtab walk_ctab_entry(const LUT &lut, uint32_t c, uint32_t ny, uint32_t nu, uint32_t tot)
 {
     const uint32_t comp = (c >= ny ? 1u : 0u) + (c >= ny + nu ? 1u : 0u);
-    return lut.hdr(6 + (int)comp) | lut.hdr(9 + (int)comp) << 15 | comp << 30;
+    WalkCtab t;
+    t.tdc = lut.tab(lut.hdr(6 + (int)comp));
+    t.tac = lut.tab(lut.hdr(9 + (int)comp));
+    t.next = c + 1u == tot ? 0u : c + 1u;
+    t.comp = comp;
+    t.m1 = comp == 1u ? 0xFFFFFFFFu : 0u;
+    t.m2 = comp == 2u ? 0xFFFFFFFFu : 0u;
+    t.pad0 = t.pad1 = 0u;
+    return t;
 }
 
 // One symbol through the two-level decode tables (entry format: b2j_internal.h). Returns the leaf, 0 = no codeword.
@@ -167,16 +194,18 @@ B2J_HD uint32_t lookup_symbol(const LUT &lut, uint32_t tab, uint32_t pk, uint32_
 // On a valid stream, from a true state, the walk follows the reference's decoder (decoder.cpp:221-260 inside the
 // loops of decoder.cpp:286-346) and ends in its state at the first symbol boundary at or behind `limit`, however the
 // symbols were grouped on the way: an AC walk-table step covers several symbols at once, and is taken only while the
-// walk is more than kWalkBitsAc - 1 bits in front of `limit` (every symbol of a group starts inside the index window)
+// walk is more than kWalkBits - 1 bits in front of `limit` (every symbol of a group starts inside the index window)
 // and the block cannot fill up in front of the group's last symbol; otherwise the first symbol of the group is taken
 // alone, and where the walk table has no entry, one symbol goes through the decode tables.
 // From any state -- true or guessed -- the result is a function of that state alone, which is all the
 // synchronisation needs (a guessed walk that reaches a state of the true walk continues exactly like it).
-// Shape: ONE loop, one table lookup per turn whatever the lane is at (DC and AC walk tables share the entry format),
-// because the lanes of a warp sit at unrelated places of their blocks: what only some lanes need -- the DC
-// bookkeeping, the switch to the next block -- is kept short, since every lane pays for it on every turn.
+// Shape: ONE loop, one table lookup per turn whatever the lane is at (DC and AC walk tables share index width and
+// entry layout; the table in use is a handle that changes behind a DC symbol and at a block switch), because the lanes
+// of a warp sit at unrelated places of their blocks: what only some lanes need -- the DC bookkeeping, the switch to
+// the next block -- is predicated and short, since the warp pays for it on nearly every turn. The bit position p is
+// the only reader state: the 64-bit window (cur:nxt) is word aligned, p & 31 is the shift.
 template <class LUT>
-B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, WalkState s, uint32_t limit, uint32_t tot)
+B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, WalkState s, uint32_t limit)
 {
     WalkResult r;
     r.nblk = 0; r.fs = kSubNone; r.fc = 0; r.dc0 = r.dc1 = r.dc2 = 0;
@@ -184,61 +213,108 @@ B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, WalkSta
     bool bad = false;
     if (p < limit)
     {
-        WalkReader br;
-        br.init(stream, p >> 3);
-        br.bitpos += p & 7u;
-        const uint32_t lim_group = limit > (uint32_t)kWalkBitsAc ? limit - (uint32_t)(kWalkBitsAc - 1) : 0u;
-        uint32_t ct = lut.ctab(c);
-        uint32_t tdc = ct & 0x7FFFu, tac = (ct >> 15) & 0x7FFFu, comp = ct >> 30;
-        while (p < limit)
+        uint32_t wi = p >> 5;
+        uint32_t cur = bswap32(stream.get(wi)), nxt = bswap32(stream.get(wi + 1u)), raw = stream.get(wi + 2u);
+        wi += 3u;
+        // two stretches: groups while every symbol of a group starts in front of `limit` (more than kWalkBits - 1
+        // bits in front of it), then single symbols up to `limit`
+        const uint32_t lim_group = limit > (uint32_t)kWalkBits ? limit - (uint32_t)(kWalkBits - 1) : 0u;
+        WalkCtab ct = lut.ctab(c);
+        uint32_t tb = z == 0u ? ct.tdc : ct.tac;
+        uint32_t fs = z == 0u ? p : kSubNone;     // where the first block of the walk starts (valid if one does)
+        r.fc = z == 0u ? c : ct.next;
+        int32_t dall = 0, d1 = 0, d2 = 0;
+        uint32_t nblk = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (uint32_t stretch = 0; stretch < 2u; stretch++)
         {
-            const uint32_t pk = br.peek();
+        const bool groups = stretch == 0u;
+        const uint32_t lim = groups ? lim_group : limit;
+        // an AC entry's first symbol is taken alone when the group does not fit the block (position + needed in 65..128)
+        // or, in the second stretch, always (position + needed in 1..127); the special entries (needed > 64) stay whole
+        const uint32_t alone_lo = groups ? 65u : 1u, alone_span = groups ? 64u : 127u;
+        while (p < lim)
+        {
+            const uint32_t pk = fsh_l(nxt, cur, p);
             const bool dc = z == 0u;
-            const uint32_t e = lut.at32((dc ? tdc : tac) + 2u * (pk >> (dc ? 32u - (uint32_t)kWalkBitsDc : 32u - (uint32_t)kWalkBitsAc)));
-            uint32_t nb, f;
-            if (e != 0u)
+            uint32_t e = lut.ld(tb, pk >> (32u - (uint32_t)kWalkBits));
+            // the whole group where it fits, else its first symbol (a DC entry is one symbol, its high half the difference)
+            const bool whole = dc || z + byte1(e) - alone_lo >= alone_span;
+            const int32_t diff = (int32_t)e >> 16;
+            if (!whole) e >>= 16;
+            uint32_t nb = e & 31u;                // bits consumed
+            uint32_t adv = byte1(e);              // scan positions advanced (a DC symbol: 1)
+            uint32_t eob = e & 0x80u;             // the set ends with the end-of-block symbol
+            int32_t dv = diff;
+            if (adv > 64u)
             {
-                // the whole group where it fits, else its first symbol (a DC entry is its own first symbol)
-                const bool group = p < lim_group && z + ((e >> 5) & 63u) <= 64u;
-                const uint32_t ee = group ? e : e >> 12;
-                nb = ee & 31u;             // bits consumed
-                f = (ee >> 5) & 127u;      // AC: scan positions advanced, >= 64 with the end-of-block flag; DC: category
-                B2J_WALK_COUNT(dc ? 3 : (group ? 0 : 1));
+                B2J_WALK_COUNT(4);
+                if (adv == kWalkEscape)
+                {
+                    // AC code longer than the index: one symbol from the prefix's sub-table
+                    const uint32_t e2 = lut.ld(tb, (e >> 16) + ((pk << (uint32_t)kWalkBits) >> (32u - nb)));
+                    nb = e2 & 31u; adv = byte1(e2); eob = e2 & 0x80u;
+                }
+                else if (adv == kWalkDcWide)
+                {
+                    // DC value bits past the index
+                    const uint32_t size = (e >> 16) & 31u;
+                    dv = extend_bits(pk << nb, size);
+                    nb += size; adv = 1u;
+                }
+                if (adv > 64u)
+                {
+                    // no walk-table entry: one symbol through the decode tables, or no codeword at all
+                    B2J_WALK_COUNT(2);
+                    const uint32_t e1 = dc ? lookup_symbol(lut, lut.hdr((int)ct.comp), pk, (uint32_t)kLutBitsDc)
+                                           : lookup_symbol(lut, lut.hdr(3 + (int)ct.comp), pk, (uint32_t)kLutBits);
+                    if (e1 == 0u)
+                    {
+                        // a block whose DC code is no codeword still counts as started: the decode lane meets the same bits and flags the image
+                        if (dc) nblk++;
+                        bad = true; stretch = 2u; break;
+                    }
+                    const uint32_t len = e1 & 31u, size = (e1 >> 6) & (dc ? 31u : 15u), run = e1 >> 10;
+                    nb = len + size;
+                    eob = (!dc && run == kRunEob) ? 0x80u : 0u;
+                    adv = (dc || eob) ? 1u : run + 1u;   // AC: zero run + the coefficient, or the extra zero of a size-0 run
+                    dv = extend_bits(pk << len, size);
+                }
             }
-            else
-            {
-                B2J_WALK_COUNT(2);
-                const uint32_t e1 = dc ? lookup_symbol(lut, lut.hdr((int)comp), pk, (uint32_t)kLutBitsDc)
-                                       : lookup_symbol(lut, lut.hdr(3 + (int)comp), pk, (uint32_t)kLutBits);
-                if (e1 == 0u) { bad = true; break; }
-                const uint32_t size = (e1 >> 6) & (dc ? 31u : 15u);
-                nb = (e1 & 31u) + size;
-                f = dc ? size : (e1 >> 10) + 1u;   // AC: zero run + the coefficient, or the extra zero of a size-0 run; EOB: run 63
-            }
-            uint32_t zn = z + f;
+            else B2J_WALK_COUNT(dc ? 3 : (whole ? 0 : 1));
             if (dc)
             {
-                // a DC code starts a block: count it, remember the first one, add its difference to the component's sum
-                const int32_t diff = extend_bits(pk << (nb - f), f);
-                if (r.nblk == 0u) { r.fs = p; r.fc = c; }
-                r.nblk++;
-                if (comp == 0u) r.dc0 += diff;
-                if (comp == 1u) r.dc1 += diff;
-                if (comp == 2u) r.dc2 += diff;
-                zn = 1u;
+                // a DC code starts a block: count it, add its difference to the sums; the AC table takes over
+                nblk++;
+                dall += dv; d1 += dv & (int32_t)ct.m1; d2 += dv & (int32_t)ct.m2;
+                tb = ct.tac;
             }
-            z = zn;
-            p += nb;
-            br.skip(nb);
-            if (z >= 64u)
+            z += adv;
+            const uint32_t pn = p + nb;
+            if ((p ^ pn) & 32u)
+            {
+                cur = nxt;
+                nxt = bswap32(raw);
+                raw = stream.get(wi);
+                wi++;
+            }
+            p = pn;
+            if (eob != 0u || z >= 64u)
             {
                 // the block is complete: next block of the MCU
                 z = 0u;
-                c = (c + 1u == tot) ? 0u : c + 1u;
+                c = ct.next;
                 ct = lut.ctab(c);
-                tdc = ct & 0x7FFFu; tac = (ct >> 15) & 0x7FFFu; comp = ct >> 30;
+                tb = ct.tdc;
+                fs = fs < p ? fs : p;
             }
         }
+        }
+        r.nblk = nblk;
+        r.fs = nblk ? fs : kSubNone;
+        r.dc0 = dall - d1 - d2; r.dc1 = d1; r.dc2 = d2;
     }
     // A non-code can only be met by a walk that started from a wrong guess (or in a corrupt stream, which the final
     // decode flags): hand the next lane the same guess a first-round walk would use instead of a dead state, so
@@ -363,6 +439,33 @@ B2J_HD bool sync_phase_need(const SyncChunk &ch, const SyncShared &sh, uint32_t 
     if (!sync_lane_active(ch, t) || t == ch.first_lane) return false;
     entry = make_uint2(sh.cur[t - 1].p, sh.cur[t - 1].cz);
     return entry.x != sh.entry_used[t].x || entry.y != sh.entry_used[t].y;
+}
+
+// Repair of a chunk whose assumed entry state was not its predecessor's exit state (k_sync_sweep; one thread): the
+// sub-sequences of the chunk are walked again in order from the true entry state until a walk leaves its sub-sequence
+// in the state the old record left it in -- from there on the old records stand, since every record is a function of
+// its entry state alone. tot4: the chunk's totals (blocks, DC sums), kept in step with the records. Returns the
+// chunk's exit state in exit_pcz (unchanged when the walks merged inside the chunk).
+template <class W>
+B2J_HD void sync_repair_chunk(const W &w, uint32_t chunk, uint32_t n_sub, uint32_t bits, SubRec *rec_img, uint2 entry,
+                              uint32_t tot4[4], uint2 &exit_pcz)
+{
+    const uint32_t first = chunk * (uint32_t)kSyncLanes;
+    const uint32_t end = first + (uint32_t)kSyncLanes < n_sub ? first + (uint32_t)kSyncLanes : n_sub;
+    for (uint32_t j = first; j < end; j++)
+    {
+        const SubRec old = rec_img[j];
+        const uint32_t lo = j * (uint32_t)(kSubBytes * 8);
+        const uint32_t hi = lo + (uint32_t)(kSubBytes * 8) < bits ? lo + (uint32_t)(kSubBytes * 8) : bits;
+        const WalkState s0 = {entry.x, entry.y & 0xFFu, entry.y >> 8};
+        const WalkResult r = w.walk(s0, hi);
+        tot4[0] += r.nblk - old.nblk;
+        tot4[1] += (uint32_t)(r.dc0 - old.dc[0]); tot4[2] += (uint32_t)(r.dc1 - old.dc[1]); tot4[3] += (uint32_t)(r.dc2 - old.dc[2]);
+        sync_set(rec_img[j], r);
+        if (r.p == old.p && r.cz == old.cz) return;   // in step with the old walks: everything behind stands
+        entry = make_uint2(r.p, r.cz);
+    }
+    exit_pcz = entry;
 }
 
 } // namespace b2j

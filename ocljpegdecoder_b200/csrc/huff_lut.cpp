@@ -90,7 +90,7 @@ bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
 
 bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out)
 {
-    const int K = is_dc ? kWalkBitsDc : kWalkBitsAc;
+    const int K = kWalkBits;
     struct Code { uint32_t code; int len; int sym; };
     Code codes[256];
     int n = 0;
@@ -115,22 +115,36 @@ bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
         }
         return nullptr;
     };
-    // 32-bit entries, stored as two u16 each (little endian): set 0 = the whole group, set 1 = its first symbol
+    auto put = [&](size_t w, uint32_t v) { out[2 * w] = (uint16_t)v; out[2 * w + 1] = (uint16_t)(v >> 16); };
+    // 32-bit entries, stored as two u16 each (little endian)
     out.assign((size_t)2 << K, 0);
+    for (uint32_t w = 0; w < (1u << K); w++) put(w, kWalkNoEntry);
     if (is_dc)
     {
-        // one symbol, both sets alike: bits consumed = code length + category, the category in the position field
         for (uint32_t w = 0; w < (1u << K); w++)
         {
             const Code *c = match(w, 0);
             if (!c || c->sym > 16) continue;
-            const uint32_t set = (uint32_t)(c->len + c->sym) | (uint32_t)c->sym << 5;
-            const uint32_t v = set | set << 12;
-            out[2 * w] = (uint16_t)v;
-            out[2 * w + 1] = (uint16_t)(v >> 16);
+            const int size = c->sym;
+            if (c->len + size > K)
+            {
+                // the value bits reach past the index: the walk extracts them itself
+                put(w, (uint32_t)c->len | kWalkDcWide << 8 | (uint32_t)size << 16);
+                continue;
+            }
+            // code and value bits inside the index: the entry carries the difference (decoder.cpp:72-82)
+            const uint32_t v = size ? (w >> (K - c->len - size)) & ((1u << size) - 1u) : 0u;
+            const int32_t diff = size == 0 ? 0 : ((v >> (size - 1)) ? (int32_t)v : (int32_t)v + 1 - (1 << size));
+            put(w, (uint32_t)(c->len + size) | 1u << 8 | (uint32_t)(uint16_t)(int16_t)diff << 16);
         }
         return true;
     }
+    auto single = [&](const Code &c) -> uint32_t {
+        const uint32_t e = c.sym == 0x00 ? 1u : 0u;
+        const uint32_t adv = e ? 1u : (uint32_t)(c.sym >> 4) + 1u, bits = (uint32_t)c.len + (e ? 0u : (uint32_t)(c.sym & 15));
+        const uint32_t half = bits | e << 7 | adv << 8;
+        return half | half << 16;
+    };
     for (uint32_t w = 0; w < (1u << K); w++)
     {
         int pos = 0, zadv = 0, nsym = 0, nbits = 0, eob = 0;
@@ -146,16 +160,44 @@ bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
                 adv = (c->sym >> 4) + 1;   // a coefficient behind `run` zeros, or run + 1 zeros when size == 0 (decoder.cpp:250-256)
                 bits = c->len + (c->sym & 15);
             }
-            if (zadv + adv + e > 63 || pos + bits > 31) break;
+            if (zadv + adv + e > 64 || pos + bits > 31) break;
             zadv += adv; pos += bits; nbits = pos; eob = e; nsym++;
-            if (nsym == 1) first = (uint32_t)nbits | (uint32_t)(zadv + eob) << 5 | (uint32_t)eob << 11;
+            if (nsym == 1) first = (uint32_t)nbits | (uint32_t)eob << 7 | (uint32_t)(zadv + eob) << 8;
             if (e) break;
         }
         if (!nsym) continue;
-        const uint32_t group = (uint32_t)nbits | (uint32_t)(zadv + eob) << 5 | (uint32_t)eob << 11;
-        const uint32_t v = group | first << 12;
-        out[2 * w] = (uint16_t)v;
-        out[2 * w + 1] = (uint16_t)(v >> 16);
+        const uint32_t group = (uint32_t)nbits | (uint32_t)eob << 7 | (uint32_t)(zadv + eob) << 8;
+        put(w, group | first << 16);
+    }
+    // codes longer than the index: one sub-table per K-bit prefix, behind the primary table (one symbol per entry)
+    std::vector<uint8_t> maxlen((size_t)1 << K, 0);
+    for (int i = 0; i < n; i++)
+        if (codes[i].len > K)
+        {
+            const uint32_t prefix = codes[i].code >> (codes[i].len - K);
+            if (maxlen[prefix] < codes[i].len) maxlen[prefix] = (uint8_t)codes[i].len;
+        }
+    std::vector<uint32_t> sub_at((size_t)1 << K, 0);
+    for (uint32_t pfx = 0; pfx < (1u << K); pfx++)
+    {
+        if (!maxlen[pfx]) continue;
+        const int nb = maxlen[pfx] - K;
+        const size_t at = out.size() / 2;
+        if (at >= 0x10000) return false;
+        sub_at[pfx] = (uint32_t)at;
+        put(pfx, (uint32_t)nb | kWalkEscape << 8 | (uint32_t)at << 16);
+        out.resize(out.size() + ((size_t)2 << nb), 0);
+        for (size_t k = 0; k < ((size_t)1 << nb); k++) put(at + k, kWalkNoEntry);
+    }
+    for (int i = 0; i < n; i++)
+    {
+        const Code &c = codes[i];
+        if (c.len <= K) continue;
+        const uint32_t pfx = c.code >> (c.len - K);
+        const int nb = maxlen[pfx] - K, extra = c.len - K;
+        const uint32_t rem = c.code & ((1u << extra) - 1u);
+        const uint32_t firstk = rem << (nb - extra), cnt = 1u << (nb - extra);
+        for (uint32_t k = 0; k < cnt; k++) put(sub_at[pfx] + firstk + k, single(c));
     }
     return true;
 }

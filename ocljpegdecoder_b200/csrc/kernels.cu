@@ -1,7 +1,7 @@
 // kernels.cu -- the sm_100a kernels of the baseline-JPEG decode path and their launchers.
 //
-//   k_scan_count / k_scan_chunks / k_unstuff_write
-//       pre-pass over the raw entropy-coded bytes: removes byte stuffing and fill bytes, finds the
+//   k_unstuff_fused
+//       single-pass pre-pass over the raw entropy-coded bytes: removes byte stuffing and fill bytes, finds the
 //       RSTn markers, checks their numbering and emits the start offset of every restart interval
 //       in the cleaned stream. Replaces read_more_data<>() (reference decoder.cpp:94-159) and the
 //       marker handling of decode_huffman_data() (decoder.cpp:289-307).
@@ -172,231 +172,7 @@ __device__ __forceinline__ uint32_t local_limit(uint32_t chunk_term, uint32_t ti
     return chunk_term <= lo ? 0u : chunk_term - lo;   // kNoTerm and anything behind the thread's bytes: no cut
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_count(const uint8_t *__restrict__ raw, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ chunk_img,
-             uint32_t *__restrict__ chunk_cnt, uint32_t *__restrict__ chunk_term, uint32_t chunk0)
-{
-    __shared__ uint32_t s_min;
-    __shared__ uint32_t s_warp[kScanThreads / 32];
-    const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x;
-    const ImgDev &im = imgs[chunk_img[c]];
-    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * (16u * kScanGroups);
-    ScanThread st;
-    st.load_classify(raw + im.raw_off, pos);
-    const uint32_t term = block_first_term(st.first_term(), tid, &s_min);
-    st.cut(local_limit(term, tid));
-    uint32_t packed = 0;
-#pragma unroll
-    for (int g = 0; g < kScanGroups; g++) packed += __popc(squeeze(st.f[g].keep)) | (__popc(squeeze(st.f[g].mark)) << 16);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
-    if ((tid & 31) == 0) s_warp[tid >> 5] = packed;
-    __syncthreads();
-    if (tid == 0)
-    {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w8 = 0; w8 < kScanThreads / 32; w8++) tot += s_warp[w8];
-        chunk_cnt[c] = tot;
-        chunk_term[c] = term;
-    }
-}
-
-// One warp per image: exclusive scan of the chunk counts, truncated at the first terminator.
-__global__ void __launch_bounds__(128)
-k_scan_chunks(const ImgDev *__restrict__ imgs, int img0, int img1, const uint32_t *__restrict__ chunk_cnt,
-              const uint32_t *__restrict__ chunk_term, uint32_t *__restrict__ chunk_base_keep,
-              uint32_t *__restrict__ chunk_base_mark, uint32_t *__restrict__ clean_len,
-              uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const int i = img0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= img1) return;
-    const ImgDev &im = imgs[i];
-    uint32_t run_keep = 0, run_mark = 0;
-    bool dead = false;
-    for (uint32_t base = 0; base < im.n_chunks; base += 32)
-    {
-        const uint32_t k = base + lane;
-        const bool valid = k < im.n_chunks;
-        uint32_t cnt = valid ? chunk_cnt[im.chunk_first + k] : 0u;
-        const bool has_term = valid && chunk_term[im.chunk_first + k] != kNoTerm;
-        const uint32_t tb = __ballot_sync(0xFFFFFFFFu, has_term);
-        const uint32_t first = tb ? (uint32_t)(__ffs(tb) - 1) : 32u;
-        const bool my_dead = dead || lane > first;
-        if (my_dead) cnt = 0;
-        uint32_t keep = cnt & 0xFFFFu, mark = cnt >> 16;
-        uint32_t ik = keep, imk = mark;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, imk, o);
-            if (lane >= (uint32_t)o) { ik += a; imk += b; }
-        }
-        if (valid)
-        {
-            chunk_base_keep[im.chunk_first + k] = my_dead ? kChunkDead : run_keep + ik - keep;
-            chunk_base_mark[im.chunk_first + k] = run_mark + imk - mark;
-        }
-        run_keep += __shfl_sync(0xFFFFFFFFu, ik, 31);
-        run_mark += __shfl_sync(0xFFFFFFFFu, imk, 31);
-        if (tb) dead = true;
-    }
-    if (lane == 0)
-    {
-        clean_len[i] = run_keep;
-        seg_start[im.seg_first] = 0;
-        // a missing RSTn makes the reference fail with "expected RSTn" (decoder.cpp:298-302)
-        if (im.has_dri && run_mark + 1 < im.n_segs) atomicOr(&status[i], B2J_ST_RST_MISMATCH);
-    }
-}
-
-// The thread's kept bytes of one 16-byte group -> shared memory at s_out[o ...]. B: the group's bytes.
-// Rare path first (a byte is stuffing, fill, a marker or behind the end of the scan): record restart
-// interval starts, squeeze dropped bytes out of the register array. Then single bytes up to the next
-// word boundary, whole words, tail bytes.
-__device__ __forceinline__ void write_group(uint8_t *__restrict__ s_out, uint32_t o, const uint32_t w[4], const ScanFlags &f,
-                                            uint32_t nkeep, uint32_t &rank, uint32_t clean_pos, const ImgDev &im, uint32_t img_idx,
-                                            uint32_t *__restrict__ seg_start, int32_t *__restrict__ status)
-{
-    uint32_t B[4] = {w[0], w[1], w[2], w[3]};
-    const uint32_t any_mark = f.mark[0] | f.mark[1] | f.mark[2] | f.mark[3];
-    if (nkeep != 16u || any_mark)
-    {
-        uint32_t keep16 = 0, mark16 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-            keep16 |= ((((f.keep[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
-            mark16 |= ((((f.mark[i] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * i);
-        }
-        while (mark16)
-        {
-            const uint32_t j = (uint32_t)__ffs(mark16) - 1u;
-            mark16 &= mark16 - 1u;
-            if (im.has_dri && rank + 1 < im.n_segs)
-            {
-                seg_start[im.seg_first + rank + 1] = clean_pos + __popc(keep16 & ((1u << j) - 1u));
-                const uint32_t wj = j < 4u ? w[0] : (j < 8u ? w[1] : (j < 12u ? w[2] : w[3]));
-                const uint32_t bj = (wj >> (8 * (j & 3u))) & 0xFFu;
-                if (bj != 0xD0u + (rank & 7u)) atomicOr(&status[img_idx], B2J_ST_RST_MISMATCH);   // decoder.cpp:298
-            }
-            rank++;
-        }
-        // squeeze the dropped bytes out, highest first (bytes above the last kept one need no move)
-        const uint32_t span = keep16 ? 32u - (uint32_t)__clz(keep16) : 0u;
-        uint32_t drop = ~keep16 & ((1u << span) - 1u);
-        while (drop)
-        {
-            const uint32_t j = 31u - (uint32_t)__clz(drop);
-            drop ^= 1u << j;
-            const uint32_t wi = j >> 2, lm = (1u << (8u * (j & 3u))) - 1u;
-            const uint32_t sh0 = __funnelshift_r(B[0], B[1], 8), sh1 = __funnelshift_r(B[1], B[2], 8),
-                           sh2 = __funnelshift_r(B[2], B[3], 8), sh3 = B[3] >> 8;
-            B[0] = wi == 0u ? ((B[0] & lm) | (sh0 & ~lm)) : B[0];
-            B[1] = wi == 1u ? ((B[1] & lm) | (sh1 & ~lm)) : (wi < 1u ? sh1 : B[1]);
-            B[2] = wi == 2u ? ((B[2] & lm) | (sh2 & ~lm)) : (wi < 2u ? sh2 : B[2]);
-            B[3] = wi == 3u ? ((B[3] & lm) | (sh3 & ~lm)) : sh3;
-        }
-    }
-    uint32_t n = nkeep;
-    const uint32_t head = min((4u - (o & 3u)) & 3u, n);
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-        if ((uint32_t)k < head) s_out[o + k] = (uint8_t)(B[0] >> (8 * k));
-    if (head)
-    {
-        const uint32_t hs = head * 8u;   // drop the head bytes from the register array
-        B[0] = __funnelshift_r(B[0], B[1], hs);
-        B[1] = __funnelshift_r(B[1], B[2], hs);
-        B[2] = __funnelshift_r(B[2], B[3], hs);
-        B[3] = B[3] >> hs;
-    }
-    o += head; n -= head;
-    uint32_t *wo = reinterpret_cast<uint32_t *>(s_out + o);
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        if ((uint32_t)(4 * k + 4) <= n) wo[k] = B[k];
-    const uint32_t full = n >> 2, tail = n & 3u;
-    const uint32_t tw = full == 0u ? B[0] : (full == 1u ? B[1] : (full == 2u ? B[2] : B[3]));
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-        if ((uint32_t)k < tail) s_out[o + full * 4u + k] = (uint8_t)(tw >> (8 * k));
-}
-
-// Writes the clean stream of one chunk: the kept bytes are compacted in shared memory (at an offset
-// congruent to their global address mod 16) and then copied out with 128-bit stores.
-__global__ void __launch_bounds__(kScanThreads, 3)
-k_unstuff_write(const uint8_t *__restrict__ raw, uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
-                const uint32_t *__restrict__ chunk_img, const uint32_t *__restrict__ chunk_term,
-                const uint32_t *__restrict__ chunk_base_keep, const uint32_t *__restrict__ chunk_base_mark,
-                uint32_t *__restrict__ seg_start, int32_t *__restrict__ status, uint32_t chunk0)
-{
-    __shared__ uint32_t s_warp[kScanThreads / 32];
-    __shared__ __align__(16) uint8_t s_out[kScanChunkBytes + 32];
-    const uint32_t c = chunk0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t base_keep = chunk_base_keep[c];
-    if (base_keep == kChunkDead) return;   // behind the end of the scan (uniform for the CTA)
-    const uint32_t img_idx = chunk_img[c];
-    const ImgDev &im = imgs[img_idx];
-    const uint32_t pos = (c - im.chunk_first) * kScanChunkBytes + tid * (16u * kScanGroups);
-    ScanThread st;
-    st.load_classify(raw + im.raw_off, pos);
-    st.cut(local_limit(chunk_term[c], tid));
-    uint32_t nkeep[kScanGroups], mine = 0;
-#pragma unroll
-    for (int g = 0; g < kScanGroups; g++)
-    {
-        nkeep[g] = __popc(squeeze(st.f[g].keep));
-        mine += nkeep[g] | (__popc(squeeze(st.f[g].mark)) << 16);
-    }
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (uint32_t)o) incl += a;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < kScanThreads / 32; k++)
-    {
-        const uint32_t v = s_warp[k];
-        before += (k < (int)warp) ? v : 0u;
-        total += v;
-    }
-    const uint32_t excl = before + incl - mine;
-    const uint32_t n_out = total & 0xFFFFu;                          // kept bytes of this chunk
-    const uint64_t g0 = im.raw_off + base_keep;                      // where they go in clean[]
-    const uint32_t a = (uint32_t)(g0 & 15u);
-    uint32_t lo = excl & 0xFFFFu;                                    // chunk-local output offset of this thread
-    uint32_t rank = chunk_base_mark[c] + (excl >> 16);               // ordinal of the next RSTn in the image
-#pragma unroll
-    for (int g = 0; g < kScanGroups; g++)
-    {
-        write_group(s_out, a + lo, st.w[g], st.f[g], nkeep[g], rank, base_keep + lo, im, img_idx, seg_start, status);
-        lo += nkeep[g];
-    }
-    __syncthreads();
-    // copy out: 16-byte vectors where whole, single bytes at the two ragged ends
-    uint8_t *gd = clean + (g0 - a);
-    const uint32_t end = a + n_out;
-    for (uint32_t v = tid; v * 16u < end; v += kScanThreads)
-    {
-        const uint32_t lo16 = v * 16u;
-        if (lo16 >= a && lo16 + 16u <= end)
-            *reinterpret_cast<uint4 *>(gd + lo16) = *reinterpret_cast<const uint4 *>(s_out + lo16);
-        else
-        {
-            const uint32_t from = lo16 < a ? a : lo16, to = lo16 + 16u < end ? lo16 + 16u : end;
-            for (uint32_t k = from; k < to; k++) gd[k] = s_out[k];
-        }
-    }
-}
-
-// ---- single-pass variant: count, prefix across the chunks of an image and write in ONE kernel.
+// ---- the pre-pass: count, prefix across the chunks of an image and write in ONE kernel.
 // Every chunk publishes a 64-bit state word: first its own totals ("aggregate"), later the totals of the
 // image up to and including itself ("inclusive"). A chunk obtains its base by looking back over its
 // predecessors' words (decoupled look-back: aggregates are added until an inclusive word is met), so no
@@ -747,111 +523,6 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
 }
 
-// Bit reader whose stream arrives through a per-lane ring in shared memory filled by cp.async (LDGSTS).
-// Why: with plain loads the look-ahead word of BitReader is the destination of a predicated LDG in nearly every
-// iteration of the decode loop (some lane of the warp always refills) and the source of the byte swap of the
-// NEXT iteration's refill. The scoreboard tracks registers per warp, not per lane, so every iteration waits for
-// the L2 round trip of the previous one -- a quarter of all stall samples of the kernel sat on that one PRMT.
-// Here no register is ever the target of a global load. The ring holds kRingChunks x 16 bytes per lane;
-// chunks are requested at the warp-synchronous point between two blocks (top_up) and one cp.async group is
-// committed there per block round, so "all groups but the newest have landed" (wait_group 1, which in steady
-// state never waits: a round is thousands of cycles) proves that everything requested in earlier rounds is
-// present. A lane that runs ahead of what is known to have landed -- a block of more than ~32 bytes -- requests
-// and waits on the spot (rare at photographic qualities; the cost is the stall the plain reader pays always).
-constexpr uint32_t kRingChunks = 4;
-constexpr uint32_t kRingBytesPerLane = kRingChunks * 16;
-
-// Out of line on purpose: the rare "ran ahead of the landed data" path must not bloat the decode loop.
-// Requests every chunk below `limit` that is still missing, waits for all of them, returns the new request mark.
-__device__ __noinline__ uint32_t ring_catch_up(uint32_t ring, const uint8_t *gbase, uint32_t req, uint32_t limit)
-{
-    while (req < limit)
-    {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + (req & (kRingBytesPerLane - 1u))), "l"(gbase + req) : "memory");
-        req += 16u;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    return req;
-}
-
-struct RingReader
-{
-    uint32_t cur, nxt;     // big-endian words: `cur` holds the bit at `bitpos`
-    uint32_t raw;          // look-ahead word (memory byte order) read from the ring one refill early
-    uint32_t bitpos;       // 0..31 after refill()
-    uint32_t w4;           // byte index (from gbase) of the next word to read from the ring
-    uint32_t w4_0;         // its value after init(): words entered into the window = (w4 - w4_0) / 4
-    uint32_t req;          // byte index up to which chunks have been requested (multiple of 16)
-    uint32_t landed;       // byte index up to which chunks are known to have landed
-    uint32_t ring;         // shared address of this lane's ring
-    const uint8_t *gbase;  // 16-byte aligned global address of stream byte 0
-
-    __device__ __forceinline__ void request_upto(uint32_t limit)
-    {
-        while (req < limit)
-        {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + (req & (kRingBytesPerLane - 1u))), "l"(gbase + req) : "memory");
-            req += 16u;
-        }
-    }
-    // the chunk that holds word w4 and the kRingChunks-1 behind it: never overwrites a chunk still to be read
-    __device__ __forceinline__ void top_up() { request_upto((w4 & ~15u) + kRingBytesPerLane); }
-    // between two blocks, all lanes of the warp together
-    __device__ __forceinline__ void round_boundary()
-    {
-        const uint32_t before = req;
-        top_up();
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        landed = before;
-    }
-    __device__ __forceinline__ void catch_up()
-    {
-        req = ring_catch_up(ring, gbase, req, (w4 & ~15u) + kRingBytesPerLane);
-        landed = req;
-    }
-    // once per symbol, in front of the window shift: the next ring word must have landed
-    __device__ __forceinline__ void ensure()
-    {
-        if (__builtin_expect(w4 >= landed, 0)) catch_up();
-    }
-    __device__ __forceinline__ uint32_t ring_word(uint32_t byte_index) const
-    {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (byte_index & (kRingBytesPerLane - 4u))) : "memory");
-        return v;
-    }
-    __device__ __forceinline__ void init(const uint8_t *p, uint32_t ring_addr)
-    {
-        const uint32_t a16 = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u);
-        gbase = p - a16;
-        ring = ring_addr;
-        req = 0u;
-        w4 = a16 & 12u;      // the word that holds p
-        catch_up();
-        cur = __byte_perm(ring_word(w4), 0, 0x0123);
-        nxt = __byte_perm(ring_word(w4 + 4u), 0, 0x0123);
-        raw = ring_word(w4 + 8u);
-        w4 += 12u;
-        w4_0 = w4 - 4u;      // `raw` has not entered the window yet
-        bitpos = (a16 & 3u) * 8u;
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, bitpos); }
-    __device__ __forceinline__ void refill()
-    {
-        if (bitpos >= 32u)
-        {
-            cur = nxt;
-            nxt = __byte_perm(raw, 0, 0x0123);
-            raw = ring_word(w4);
-            w4 += 4u;
-            bitpos -= 32u;
-        }
-    }
-    __device__ __forceinline__ uint32_t words_consumed() const { return (w4 - 4u - w4_0) >> 2; }
-};
-
 // One symbol from a two-level LUT in shared memory (entry format: b2j_internal.h). `tab` is the
 // shared-window byte address of the table. Returns the leaf entry, 0 when no codeword matches.
 __device__ __forceinline__ uint32_t lut_first(uint32_t tab, uint32_t pk, uint32_t bits = kLutBits)
@@ -885,10 +556,7 @@ __device__ __forceinline__ int32_t extend_sz(uint32_t v, uint32_t size)
 //   position, MCU phase, block index and DC predictors come from the self-synchronisation passes
 //   (SubRec / SubPre), and the table choice is per lane.
 constexpr uint32_t kZzBytes = 192;   // 128 zig-zag offsets + 64 bytes of scratch for the CTA-wide prefix of the SYNC lanes
-template <bool RING> struct ReaderOf { typedef BitReader<1> type; };
-template <> struct ReaderOf<true> { typedef RingReader type; };
-
-template <bool WIDE, bool DEFER, bool SYNC>
+template <bool SYNC>
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const HuffCtaDev *__restrict__ ctas,
               const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ clean_len,
@@ -900,8 +568,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint8_t *s_slots = smem;
     uint8_t *s_zz2 = smem + kHuffThreads * 128;                 // lanes sit at different scan positions: shared, not constant, memory;
                                                                 // 128 entries: a corrupt block may run up to 15 positions past 63
-    constexpr uint32_t kRingBytes = WIDE ? kHuffThreads * kRingBytesPerLane : 0;   // [ ... ][ per-lane stream rings ][ LUT set ]
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + kZzBytes + kRingBytes);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kHuffThreads * 128 + kZzBytes);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -987,10 +654,8 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         decodable = active && nblk > 0;
     }
 
-    typename ReaderOf<WIDE>::type br;
-    const uint8_t *base = clean + im.raw_off;
-    if (WIDE) reinterpret_cast<RingReader &>(br).init(base + (decodable ? start : 0u), smem_addr(smem) + kHuffThreads * 128 + kZzBytes + tid * kRingBytesPerLane);
-    else reinterpret_cast<BitReader<1> &>(br).init(base, decodable ? start : 0u);
+    BitReader<1> br;
+    br.init(clean + im.raw_off, decodable ? start : 0u);
     const uint32_t bit0 = br.bitpos;          // consumed bits are counted from byte `start`
     const uint32_t seg_bytes = end > start ? end - start : 0u;   // !SYNC: what the lane may consume
     if (SYNC) br.bitpos += start_bit & 7u;
@@ -999,7 +664,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint32_t sm_base;   // kept opaque: otherwise the shared-window base is re-derived (S2R) inside the decode loop
     asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_addr(smem)));
     const uint32_t sm_zz = sm_base + kHuffThreads * 128;
-    const uint32_t sm_lut = sm_zz + kZzBytes + kRingBytes;
+    const uint32_t sm_lut = sm_zz + kZzBytes;
     // shared address of this lane's slot with the chunk swizzle folded in: coefficient n lives at
     // slot + ((n>>3) ^ (lane&7))*16 + (n&7)*2 == slot_key ^ (2n)   (slots are 128-byte aligned)
     const uint32_t slot_key = sm_base + tid * 128u + ((lane & 7u) << 4);
@@ -1015,7 +680,6 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
         if (mine && !dead)
         {
             // ---- DC (decoder.cpp:226-233)
-            if (WIDE) reinterpret_cast<RingReader &>(br).ensure();
             uint32_t pk = br.peek();
             uint32_t e = lut_first(dc_tab, pk, kLutBitsDc);
             if (!(e & 32u)) e = lut_second(dc_tab, pk, e, kLutBitsDc);
@@ -1037,8 +701,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
                 uint32_t pos = 1;
                 while (true)
                 {
-                    if (WIDE) reinterpret_cast<RingReader &>(br).ensure();
-                    pk = br.peek();
+                            pk = br.peek();
                     e = lut_first(ac_tab, pk);
                     if (!(e & 32u))
                     {
@@ -1078,13 +741,12 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
             }
         }
         __syncwarp();
-        if (WIDE) reinterpret_cast<RingReader &>(br).round_boundary();
         // A lane whose segment is truncated or corrupt must not keep reading whatever follows it (other images,
         // the scratch arrays, the end of the allocation): once it has fetched more than its segment holds, plus the
         // reader's look-ahead, it stops and the image is flagged (decoder.cpp:310-314 "data incomplete").
         if (!SYNC && !dead)
         {
-            const uint32_t nw_now = WIDE ? br.words_consumed() : reinterpret_cast<BitReader<1> &>(br).words_fetched();
+            const uint32_t nw_now = br.words_fetched();
             if (nw_now * 4u > seg_bytes + 16u) { err |= B2J_ST_OVERRUN; dead = true; }
         }
         bi = (bi + 1 == tot) ? 0u : bi + 1;
@@ -1094,7 +756,7 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     {
         // bits consumed since `start`; a restart interval must end exactly at its marker
         // (decoder.cpp:296-302 aligns to the byte boundary and expects RSTn there)
-        const uint32_t nw = WIDE ? br.words_consumed() : reinterpret_cast<BitReader<1> &>(br).words_fetched();
+        const uint32_t nw = br.words_fetched();
         const uint64_t bits = (uint64_t)nw * 32u + br.bitpos - bit0;
         const uint64_t used = (bits + 7u) >> 3;
         const uint64_t avail = (uint64_t)end - start;
@@ -1123,30 +785,38 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 // the LUT set staged in shared memory, addressed through the 32-bit shared window.
 struct DevLut
 {
-    uint32_t sm;            // shared-window byte address of the set
-    uint32_t ct;            // shared-window byte address of the per-block-index table (walk_ctab_entry)
-    const uint16_t *s;      // the set as a pointer (header reads outside the loops)
-    __device__ __forceinline__ uint32_t at(uint32_t i) const { return lds_u16(sm + (i << 1)); }
-    __device__ __forceinline__ uint32_t at32(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm + (i << 1))); return v; }
-    __device__ __forceinline__ uint32_t ctab(uint32_t c) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ct + (c << 2))); return v; }
-    __device__ __forceinline__ uint32_t hdr(int i) const { return s[i]; }
+    uint32_t sm;            // shared-window byte address of the WALK part of the set (what the sync kernels stage)
+    uint32_t walk0;         // u16 offset of the walk part inside the set
+    uint32_t ct;            // shared-window byte address of the per-block table (WalkCtab[16])
+    const uint16_t *g;      // the whole set in global memory: header and decode tables (the rare one-symbol path)
+    __device__ __forceinline__ uint32_t at(uint32_t i) const { return __ldg(g + i); }
+    __device__ __forceinline__ uint32_t tab(uint32_t off16) const { return sm + ((off16 - walk0) << 1); }
+    __device__ __forceinline__ uint32_t ld(uint32_t h, uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(h + (i << 2))); return v; }
+    __device__ __forceinline__ WalkCtab ctab(uint32_t c) const
+    {
+        WalkCtab t;
+        const uint32_t a = ct + c * (uint32_t)sizeof(WalkCtab);
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.tdc), "=r"(t.tac), "=r"(t.next), "=r"(t.comp) : "r"(a));
+        asm("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(t.m1), "=r"(t.m2) : "r"(a));
+        t.pad0 = t.pad1 = 0u;
+        return t;
+    }
+    __device__ __forceinline__ uint32_t hdr(int i) const { return __ldg(g + i); }
 };
 
 struct DevWalk
 {
     StreamWords stream;
     DevLut lut;
-    uint32_t tot;
-    // s_ctab: 16 words of shared memory, filled here by the first `tot` threads (the caller synchronises afterwards)
-    __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_lut, const uint16_t *s_lut, uint32_t *s_ctab, const ImgDev &im)
+    // s_ctab: 16 WalkCtab of shared memory, filled here by the first `tot` threads (the caller synchronises afterwards)
+    __device__ __forceinline__ void init(const uint8_t *clean_img, uint32_t sm_walk, const uint16_t *g_lut, WalkCtab *s_ctab, const ImgDev &im)
     {
         stream.w = reinterpret_cast<const uint32_t *>(clean_img);
-        lut.sm = sm_lut; lut.s = s_lut;
+        lut.sm = sm_walk; lut.g = g_lut; lut.walk0 = im.lut_dec_len;
         asm volatile("mov.u32 %0, %1;" : "=r"(lut.ct) : "r"(smem_addr(s_ctab)));   // opaque: otherwise the window base is re-derived inside the loop
-        tot = im.tot_blks;
-        if (threadIdx.x < tot && threadIdx.x < 16u) s_ctab[threadIdx.x] = walk_ctab_entry(lut, threadIdx.x, im.ny_blks, im.nu_blks);
+        if (threadIdx.x < im.tot_blks && threadIdx.x < 16u) s_ctab[threadIdx.x] = walk_ctab_entry(lut, threadIdx.x, im.ny_blks, im.nu_blks, im.tot_blks);
     }
-    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit, tot); }
+    __device__ __forceinline__ WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit); }
 };
 
 // ---- chunk-wise synchronisation (b2j_sync.h): all rounds of a chunk of kSyncLanes sub-sequences inside one CTA.
@@ -1213,11 +883,12 @@ __device__ __forceinline__ void sync_run_chunk(const DevWalk &wk, SyncShared &sh
     __syncthreads();   // s_wtot and sh may be reused by the caller
 }
 
+// The walk part of the image's LUT set (the walk tables; the decode part stays in global memory) into shared memory.
 __device__ __forceinline__ void sync_stage_lut(uint16_t *s_lut, const uint16_t *__restrict__ luts, const ImgDev &im)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off);
+    const uint4 *src = reinterpret_cast<const uint4 *>(luts + im.lut_off + im.lut_dec_len);
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-    for (uint32_t k = threadIdx.x; k < im.lut_len / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
+    for (uint32_t k = threadIdx.x; k < (im.lut_len - im.lut_dec_len) / 8; k += kHuffThreads) dst[k] = __ldg(src + k);
 }
 
 // One CTA per chunk. use_pre: walk kSyncPre sub-sequences in front of the chunk to find its entry state (0: every chunk
@@ -1229,7 +900,7 @@ k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_wtot[kHuffThreads / 32];
-    __shared__ uint32_t s_ctab[16];
+    __shared__ __align__(16) WalkCtab s_ctab[16];
     SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
     const HuffCtaDev cta = ctas[blockIdx.x];
@@ -1247,7 +918,7 @@ k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
     uint32_t sm_lut;
     asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
     DevWalk wk;
-    wk.init(clean + im.raw_off, sm_lut, s_lut, s_ctab, im);
+    wk.init(clean + im.raw_off, sm_lut, luts + im.lut_off, s_ctab, im);
     __syncthreads();
     SyncChunk ch;
     ch.first = cta.seg_first; ch.n_sub = n_sub; ch.bits = bits;
@@ -1268,7 +939,7 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_wtot[kHuffThreads / 32];
-    __shared__ uint32_t s_ctab[16];
+    __shared__ __align__(16) WalkCtab s_ctab[16];
     __shared__ uint32_t s_min;
     SyncShared &sh = *reinterpret_cast<SyncShared *>(smem);
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem + kSyncSharedBytes);
@@ -1313,15 +984,19 @@ k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs,
         uint32_t sm_lut;
         asm volatile("mov.u32 %0, %1;" : "=r"(sm_lut) : "r"(smem_addr(smem) + kSyncSharedBytes));
         DevWalk wk;
-        wk.init(clean + im.raw_off, sm_lut, s_lut, s_ctab, im);
+        wk.init(clean + im.raw_off, sm_lut, luts + im.lut_off, s_ctab, im);
         __syncthreads();
-        const uint4 prev = __ldcg(state + found - 1u);
-        SyncChunk ch;
-        ch.first = found * (uint32_t)kSyncLanes; ch.n_sub = n_sub; ch.bits = bits;
-        ch.first_lane = (uint32_t)kSyncPre;
-        ch.forced = true;
-        ch.forced_entry = make_uint2(prev.z, prev.w);
-        sync_run_chunk(wk, sh, ch, recs + im.sub_first, state + found, tot + found, nullptr, s_wtot);
+        if (tid == 0)
+        {
+            // one thread chases the change downstream; nearly always the first walk already falls into step
+            const uint4 prev = __ldcg(state + found - 1u), mine = __ldcg(state + found);
+            const uint4 t = __ldcg(tot + found);
+            uint32_t t4[4] = {t.x, t.y, t.z, t.w};
+            uint2 exit_pcz = make_uint2(mine.z, mine.w);
+            sync_repair_chunk(wk, found, n_sub, bits, recs + im.sub_first, make_uint2(prev.z, prev.w), t4, exit_pcz);
+            __stcg(tot + found, make_uint4(t4[0], t4[1], t4[2], t4[3]));
+            __stcg(state + found, make_uint4(prev.z, prev.w, exit_pcz.x, exit_pcz.y));
+        }
         __threadfence_block();
         __syncthreads();
         repaired++;
@@ -1965,18 +1640,16 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
 
 // =====================================================================================
 // Launchers (host).
-size_t huff_smem_bytes(uint32_t max_lut_len, bool ring) { return (size_t)kHuffThreads * 128 + kZzBytes + (ring ? (size_t)kHuffThreads * kRingBytesPerLane : 0) + (size_t)max_lut_len * 2; }
+size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128 + kZzBytes + (size_t)max_lut_len * 2; }
 
 cudaError_t configure_kernels(uint32_t max_lut_len)
 {
-    const int hb = (int)huff_smem_bytes(kLutMaxDecode, true);   // the decode kernels stage the decode part of a LUT set only
-    cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
+    const int hb = (int)huff_smem_bytes(kLutMaxDecode);   // the decode kernels stage the decode part of a LUT set only
+    cudaError_t e = cudaFuncSetAttribute(k_huff_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
+    e = cudaFuncSetAttribute(k_huff_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_huff_decode<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hb);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sync_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSyncSharedBytes + max_lut_len * 2));
+    e = cudaFuncSetAttribute(k_sync_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSyncSharedBytes + max_lut_len * 2));   // the walk part of a set is staged
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sync_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSyncSharedBytes + max_lut_len * 2));
     if (e != cudaSuccess) return e;
@@ -2003,29 +1676,15 @@ void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t nc = r.chunk1 - r.chunk0, ni = r.img1 - r.img0;
     if (nc == 0 || ni == 0) return;
-    if (a.prepass_fused)
-    {
-        k_unstuff_fused<<<nc, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_state, a.clean_len, a.seg_start, a.status, r.chunk0);
-        return;
-    }
-    k_scan_count<<<nc, kScanThreads, 0, s>>>(a.raw, a.imgs, a.chunk_img, a.chunk_cnt, a.chunk_term, r.chunk0);
-    k_scan_chunks<<<(ni + 3) / 4, 128, 0, s>>>(a.imgs, (int)r.img0, (int)r.img1, a.chunk_cnt, a.chunk_term, a.chunk_base_keep,
-                                               a.chunk_base_mark, a.clean_len, a.seg_start, a.status);
-    k_unstuff_write<<<nc, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_term, a.chunk_base_keep,
-                                                a.chunk_base_mark, a.seg_start, a.status, r.chunk0);
+    k_unstuff_fused<<<nc, kScanThreads, 0, s>>>(a.raw, a.clean, a.imgs, a.chunk_img, a.chunk_state, a.clean_len, a.seg_start, a.status, r.chunk0);
 }
 
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
 {
     const uint32_t n = r.cta1 - r.cta0;
     if (n == 0) return;
-    const size_t sm = huff_smem_bytes(a.max_lut_dec_len, false);
-    if (a.huff_variant & 1u)
-        k_huff_decode<true, false, false><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len, true), s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
-                                                                    a.coef, a.status, nullptr, nullptr);
-    else
-        k_huff_decode<false, false, false><<<n, kHuffThreads, sm, s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
-                                                                     a.coef, a.status, nullptr, nullptr);
+    k_huff_decode<false><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len), s>>>(a.clean, a.imgs, a.huff_ctas + r.cta0, a.seg_start, a.clean_len, a.luts,
+                                                                                     a.coef, a.status, nullptr, nullptr);
 }
 
 // Streams without restart markers: chunk-wise synchronisation, the sweep, the scan, then the decode.
@@ -2033,13 +1692,13 @@ void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s
 {
     const uint32_t n = r.scta1 - r.scta0, ni = r.simg1 - r.simg0;
     if (n == 0 || ni == 0) return;
-    const size_t sync_bytes = kSyncSharedBytes + (size_t)a.max_lut_len * 2;
+    const size_t sync_bytes = kSyncSharedBytes + (size_t)a.max_lut_walk_len * 2;
     k_sync_chunks<<<n, kHuffThreads, sync_bytes, s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.clean_len, a.luts, a.recs, a.sync_chunk_state + r.scta0,
                                                       a.sync_cta_base + r.scta0, a.sync_stats, a.sync_use_pre ? 1u : 0u);
     k_sync_sweep<<<ni, kHuffThreads, sync_bytes, s>>>(a.clean, a.imgs, a.sync_imgs + r.simg0, a.clean_len, a.luts, a.recs, a.sync_chunk_state + r.scta0,
                                                      a.sync_cta_base + r.scta0, a.sync_stats, r.scta0);
     k_sync_cta_scan<<<ni, 32, 0, s>>>(a.imgs, a.sync_imgs + r.simg0, a.sync_cta_base + r.scta0, r.scta0);
-    k_huff_decode<false, false, true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len, false), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
+    k_huff_decode<true><<<n, kHuffThreads, huff_smem_bytes(a.max_lut_dec_len), s>>>(a.clean, a.imgs, a.sync_ctas + r.scta0, a.seg_start,
                                                                                            a.clean_len, a.luts, a.coef, a.status, a.recs, a.sync_cta_base + r.scta0);
 }
 

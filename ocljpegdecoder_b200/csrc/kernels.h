@@ -25,8 +25,7 @@ struct DecodeArgs
     const CUtensorMap *tmap;   // host copy, passed by value to the kernel
     // scratch
     uint8_t *clean;
-    uint32_t *chunk_cnt, *chunk_term, *chunk_base_keep, *chunk_base_mark;   // three-kernel pre-pass (B2J_PREPASS=3)
-    uint64_t *chunk_state;   // single-pass pre-pass: look-back words, zeroed before every decode
+    uint64_t *chunk_state;   // pre-pass: look-back words, zeroed before every decode
     uint32_t *clean_len, *seg_start;
     SubRec *recs;           // self-synchronising path: one record per sub-sequence
     uint4 *sync_cta_base;   // per chunk (= decode CTA) of the self-synchronising path: (blocks started, DC sums), then their prefix
@@ -38,12 +37,10 @@ struct DecodeArgs
     uint8_t *pixels;
     int32_t *status;
     // sizes
-    uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len, max_lut_dec_len;   // LUT set lengths: whole / decode part
+    uint32_t n_images, n_chunks, n_huff_ctas, n_tiles, max_lut_len, max_lut_dec_len, max_lut_walk_len;   // LUT set lengths: whole / decode part / walk part
     int out_format;          // B2J_OUT_*: layout of the pixel plane (b2j_batch_set_output_format)
     bool use_tma;
     bool any_wide_q;         // some quantiser of the batch exceeds 255 (16-bit DQT): generic dequantisation
-    bool prepass_fused;      // single-pass pre-pass (default); B2J_PREPASS=3 selects the three-kernel one
-    uint32_t huff_variant;   // bit 0: stream through the per-lane cp.async rings (default); B2J_HUFF_VARIANT=0: plain loads
 };
 
 // A contiguous group of images of a batch: the unit the two-stream pipeline works on.
@@ -53,8 +50,8 @@ struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1
 
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
-size_t huff_smem_bytes(uint32_t max_lut_len, bool ring);
-void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 3 kernels
+size_t huff_smem_bytes(uint32_t max_lut_len);
+void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
 void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 4 kernels
 constexpr int kSyncLaunches = 4;

@@ -15,10 +15,16 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -112,7 +118,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_chunk_cnt, off_chunk_term, off_chunk_bk, off_chunk_bm, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states;
+    size_t off_clean, off_clean_end, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -354,7 +360,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     static const uint8_t zz[64] = B2J_ZIGZAG_TABLE;
 
     size_t raw_total = 0, pix_total = 0, blk_total = 0;
-    uint32_t seg_total = 0, max_lut_len = 0, max_lut_dec_len = 0;
+    uint32_t seg_total = 0, max_lut_len = 0, max_lut_dec_len = 0, max_lut_walk_len = 0;
     int64_t pixels = 0, scan_bytes = 0;
     int rc = B2J_OK;
     for (int i = 0; i < n && rc == B2J_OK; i++)
@@ -452,6 +458,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         im.lut_dec_len = it->second.dec_len;
         if (im.lut_len > max_lut_len) max_lut_len = im.lut_len;
         if (im.lut_dec_len > max_lut_dec_len) max_lut_dec_len = im.lut_dec_len;
+        if (im.lut_len - im.lut_dec_len > max_lut_walk_len) max_lut_walk_len = im.lut_len - im.lut_dec_len;
         pixels += (int64_t)d.width * d.height;
         scan_bytes += (int64_t)d.scan_size;
     }
@@ -509,10 +516,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     // ---- scratch layout
     off = 0;
     b->off_clean = place(raw_total + 256);   // the bit readers prefetch up to 48 bytes past a segment
-    b->off_chunk_cnt = place(4 * chunk_img.size());
-    b->off_chunk_term = place(4 * chunk_img.size());
-    b->off_chunk_bk = place(4 * chunk_img.size());
-    b->off_chunk_bm = place(4 * chunk_img.size());
+    b->off_clean_end = off;
     b->off_clean_len = place(4 * (size_t)n);
     b->off_seg_start = place(4 * (size_t)seg_total);
     b->off_status = place(4 * (size_t)n);
@@ -579,10 +583,6 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.qtabs = reinterpret_cast<const uint16_t *>(b->d_blob + b->off_qtabs);
     a.tmap = &b->tmap;
     a.clean = b->d_scratch + b->off_clean;
-    a.chunk_cnt = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_cnt);
-    a.chunk_term = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_term);
-    a.chunk_base_keep = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bk);
-    a.chunk_base_mark = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_chunk_bm);
     a.chunk_state = reinterpret_cast<uint64_t *>(b->d_scratch + b->off_chunk_state);
     a.clean_len = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_clean_len);
     a.seg_start = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_seg_start);
@@ -595,15 +595,12 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     a.n_tiles = (uint32_t)tiles.size();
     a.max_lut_len = max_lut_len;
     a.max_lut_dec_len = max_lut_dec_len;
+    a.max_lut_walk_len = max_lut_walk_len;
     a.use_tma = ctx->use_tma;
     a.out_format = B2J_OUT_BGRA;
     a.any_wide_q = false;
     for (const ImgDev &im : b->imgs) a.any_wide_q = a.any_wide_q || im.wide_q != 0;
     {
-        const char *pp = getenv("B2J_PREPASS");
-        a.prepass_fused = !(pp && atoi(pp) == 3);
-        const char *hv = getenv("B2J_HUFF_VARIANT");
-        a.huff_variant = hv ? (uint32_t)atoi(hv) : 0u;
         const char *sp = getenv("B2J_SYNC_PRE");
         a.sync_use_pre = !(sp && atoi(sp) == 0);
     }
@@ -613,7 +610,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     inf.n_images = n;
     int idct_launches = 0;
     for (const PartRange &pr : b->parts) idct_launches += (pr.tile_mid > pr.tile0 ? 1 : 0) + (pr.tile_gen > pr.tile_mid ? 1 : 0) + (pr.tile1 > pr.tile_gen ? 1 : 0);
-    inf.kernel_launches = idct_launches + (int32_t)b->parts.size() * ((a.prepass_fused ? 1 : 3) + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
+    inf.kernel_launches = idct_launches + (int32_t)b->parts.size() * (1 + (ctas.empty() ? 0 : 1) + (sctas.empty() ? 0 : kSyncLaunches));
     inf.total_pixels = pixels;
     inf.total_blocks = (int64_t)blk_total;
     inf.scan_bytes = scan_bytes;
@@ -656,7 +653,7 @@ extern "C" int b2j_batch_upload(b2j_batch *b, void *stream)
     {
         // padding rows of the plane and the tail of the clean stream are read (never used); define them once
         CU_TRY(cudaMemsetAsync(b->d_coef + (b->coef_rows - kTileBlocks) * 64, 0, (size_t)kTileBlocks * 128, s));
-        CU_TRY(cudaMemsetAsync(b->d_scratch + b->off_clean, 0, b->off_chunk_cnt - b->off_clean, s));
+        CU_TRY(cudaMemsetAsync(b->d_scratch + b->off_clean, 0, b->off_clean_end - b->off_clean, s));
         b->uploaded = true;
     }
     return B2J_OK;
@@ -679,7 +676,7 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
     CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
     CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
     CU_TRY(cudaMemsetAsync(a.sync_stats, 0, 4 * 8, s));
-    if (a.prepass_fused) CU_TRY(cudaMemsetAsync(a.chunk_state, 0, 8 * (size_t)a.n_chunks, s));
+    CU_TRY(cudaMemsetAsync(a.chunk_state, 0, 8 * (size_t)a.n_chunks, s));
     const size_t np = b->parts.size();
     for (size_t p = 0; p < np; p++)
     {
@@ -872,87 +869,318 @@ extern "C" int b2j_batch_read_coefs(b2j_batch *b, void *stream, int image, int32
     return B2J_OK;
 }
 
-extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, int gate,
-                               uint8_t *const *out_bgra, int32_t *status)
+// ---------------------------------------------------------------------------------------
+// Host feed: b2j_decode_host_ex / _multi, pinned buffers, file reader.
+
+namespace {
+
+// Buffers back to the pools without a stream synchronisation: the caller has seen the event that closes the batch's work.
+void destroy_batch_done(b2j_batch *b)
 {
-    if (!ctx || n <= 0 || !files || !lens || !out_bgra || !status) return B2J_E_ARG;
-    CU_TRY(cudaSetDevice(ctx->device));
-    // Pipelined over groups of images: while group g's pixels travel device->host on the second stream,
-    // group g+1 is parsed and staged on the host, uploaded and decoded on the first stream. The D2H copy
-    // of the BGRA pixels is what bounds this call (PCIe), everything else hides behind it.
-    // Headers are parsed group by group, not all up front: the first pixels should be on their way early.
-    std::vector<int> ok_idx;
-    ok_idx.reserve((size_t)n);
-    const char *ge = getenv("B2J_HOST_GROUP");
-    size_t group = ge ? (size_t)atoi(ge) : 32;   // measured on B200 (tests/e2e_probe.py): with the ramp below 32 .. 64 images per group are best
-    if (group < 1) group = 1;
-    struct Group { b2j_batch *b; size_t first, count; cudaEvent_t decoded; };
-    std::vector<Group> groups;
+    destroy_events(b);
+    release_batch_buffers(b);
+    delete b;
+}
+
+int auto_threads(int asked, int cap)
+{
+    if (asked > 0) return asked < 64 ? asked : 64;
+    const unsigned hw = std::thread::hardware_concurrency();
+    int t = hw ? (int)hw : 4;
+    return t < cap ? t : cap;
+}
+
+struct FeedGroup
+{
+    int first = 0, count = 0;            // file index range
+    b2j_batch *b = nullptr;              // built by a worker; nullptr when no file of the group was accepted
+    std::vector<int> idx;                // file index of every image of the batch
     int rc = B2J_OK;
-    // The first groups are small (2, 4, 8, ... images): nothing travels device->host before the first group is
-    // parsed, staged, uploaded and decoded, so that lead time is kept short; later groups are `group` images.
-    const char *re = getenv("B2J_HOST_RAMP");
-    size_t ramp = (re && atoi(re) == 0) ? group : 2;
-    int next = 0;   // next file to parse
-    std::vector<b2j_image_desc> d;
-    std::vector<const uint8_t *> f;
-    std::vector<size_t> l;
-    while (next < n && rc == B2J_OK)
+    std::string err;
+    bool ready = false;                  // set by the worker under the feed mutex
+    bool parsed = false;                 // the header verdicts of its files are in status[]
+    cudaEvent_t decoded = nullptr, done = nullptr;
+    bool closed = false;
+};
+
+} // namespace
+
+extern "C" int b2j_decode_host_ex(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, const b2j_host_opts *opts,
+                                  uint8_t *const *out, int32_t *status)
+{
+    if (!ctx || n <= 0 || !files || !lens || !out || !status || !opts) return B2J_E_ARG;
+    const int fmt = opts->out_format;
+    if (fmt != B2J_OUT_BGRA && fmt != B2J_OUT_RGB24 && fmt != B2J_OUT_RGB_PLANAR) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int gate = opts->gate;
+    const int group = opts->group > 0 ? opts->group : 32;
+    const int n_threads = auto_threads(opts->n_threads, 8);
+
+    // Groups of consecutive files. The first groups are small (2, 4, 8, ...): nothing travels device->host before the
+    // first group is parsed, staged, uploaded and decoded, so that lead time is kept short.
+    std::vector<FeedGroup> groups;
+    for (int next = 0, ramp = 2; next < n; ramp *= 2)
     {
-        const size_t step = ramp < group ? ramp : group;
-        ramp *= 2;
-        const size_t g0 = ok_idx.size();
-        d.clear(); f.clear(); l.clear();
-        while (next < n && d.size() < step)
+        FeedGroup g;
+        g.first = next;
+        g.count = std::min(n - next, std::min(ramp, group));
+        next += g.count;
+        groups.push_back(std::move(g));
+        if (ramp > group) ramp = group;
+    }
+    const int ng = (int)groups.size();
+
+    // per-image status words come back through one pinned array, copied behind each group's pixels
+    int32_t *h_status = nullptr; size_t h_status_cap = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaError_t e = ctx->pin_pool.get(4 * (size_t)n, (void **)&h_status, &h_status_cap);
+        if (e != cudaSuccess) { cudaGetLastError(); return B2J_E_NOMEM; }
+    }
+
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> next_group(0);
+    int consumed = 0;                    // groups the enqueueing thread has taken (under mu)
+    bool stop = false;
+    const int window = n_threads + 2;    // groups built ahead of the enqueueing thread: bounds the pinned staging in flight
+
+    auto worker = [&]() {
+        cudaSetDevice(ctx->device);
+        std::vector<b2j_image_desc> d;
+        std::vector<const uint8_t *> f;
+        std::vector<size_t> l;
+        for (;;)
         {
-            b2j_image_desc desc;
-            const int prc = b2j_parse_header(files[next], lens[next], gate, &desc);
-            status[next] = prc;
-            if (prc == B2J_OK) { ok_idx.push_back(next); d.push_back(desc); f.push_back(files[next]); l.push_back(lens[next]); }
-            next++;
+            const int g = next_group.fetch_add(1);
+            if (g >= ng) return;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || g < consumed + window; });
+                if (stop) { groups[(size_t)g].ready = true; cv.notify_all(); continue; }
+            }
+            FeedGroup &G = groups[(size_t)g];
+            d.clear(); f.clear(); l.clear();
+            for (int i = G.first; i < G.first + G.count; i++)
+            {
+                b2j_image_desc desc;
+                const int prc = b2j_parse_header(files[i], lens[i], gate, &desc);
+                status[i] = prc;
+                if (prc == B2J_OK) { G.idx.push_back(i); d.push_back(desc); f.push_back(files[i]); l.push_back(lens[i]); }
+            }
+            G.parsed = true;
+            if (!d.empty())
+            {
+                G.rc = b2j_batch_create(ctx, (int)d.size(), d.data(), f.data(), l.data(), &G.b);
+                if (G.rc != B2J_OK) G.err = t_last_error;
+                else G.b->args.out_format = fmt;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                G.ready = true;
+            }
+            cv.notify_all();
         }
-        const size_t cnt = d.size();
-        if (cnt == 0) break;
-        Group gr{nullptr, g0, cnt, nullptr};
-        rc = b2j_batch_create(ctx, (int)cnt, d.data(), f.data(), l.data(), &gr.b);
-        if (rc != B2J_OK) break;
-        groups.push_back(gr);
-        Group &G = groups.back();
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+
+    int rc = B2J_OK;
+    int oldest = 0;   // first group whose buffers are still held
+    auto close_group = [&](FeedGroup &G) {
+        if (G.closed) return;
+        G.closed = true;
+        if (G.b)
+        {
+            for (size_t k = 0; k < G.idx.size(); k++) status[G.idx[k]] = h_status[G.idx[k]];
+            destroy_batch_done(G.b);
+            G.b = nullptr;
+        }
+        if (G.decoded) cudaEventDestroy(G.decoded);
+        if (G.done) cudaEventDestroy(G.done);
+        G.decoded = G.done = nullptr;
+    };
+    for (int g = 0; g < ng && rc == B2J_OK; g++)
+    {
+        FeedGroup &G = groups[(size_t)g];
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return G.ready; });
+            consumed = g + 1;
+        }
+        cv.notify_all();
+        if (G.rc != B2J_OK) { rc = G.rc; t_last_error = G.err; break; }
+        if (!G.b) { G.closed = true; continue; }
         if ((rc = b2j_batch_upload(G.b, ctx->stream)) != B2J_OK) break;
         if ((rc = b2j_batch_decode(G.b, ctx->stream)) != B2J_OK) break;
         cudaError_t e = cudaEventCreateWithFlags(&G.decoded, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(G.decoded, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, G.decoded, 0);
-        if (e != cudaSuccess) { rc = fail_cuda(e, "event"); break; }
-        for (size_t k = 0; k < cnt && rc == B2J_OK; k++)
+        for (size_t k = 0; k < G.idx.size() && e == cudaSuccess; k++)
         {
             const ImgDev &im = G.b->imgs[k];
-            uint8_t *dst = out_bgra[ok_idx[g0 + k]];
-            if (!dst) continue;
-            e = cudaMemcpyAsync(dst, G.b->d_pix + im.pix_off, (size_t)im.width * im.height * 4, cudaMemcpyDeviceToHost, ctx->stream2);
-            if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyAsync D2H");
+            uint8_t *dst = out[G.idx[k]];
+            if (dst) e = cudaMemcpyAsync(dst, G.b->d_pix + im.pix_off, image_bytes(G.b, im), cudaMemcpyDeviceToHost, ctx->stream2);
+        }
+        // the status words of the group's images land at their file indices (consecutive only when no file was refused)
+        for (size_t k = 0; k < G.idx.size() && e == cudaSuccess;)
+        {
+            size_t k1 = k + 1;
+            while (k1 < G.idx.size() && G.idx[k1] == G.idx[k1 - 1] + 1) k1++;
+            e = cudaMemcpyAsync(h_status + G.idx[k], G.b->args.status + k, 4 * (k1 - k), cudaMemcpyDeviceToHost, ctx->stream2);
+            k = k1;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(G.done, ctx->stream2);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "b2j_decode_host_ex enqueue"); break; }
+        // groups whose pixels have arrived give their buffers back to the pools for the groups still to come
+        while (oldest < g)
+        {
+            FeedGroup &O = groups[(size_t)oldest];
+            if (!O.closed)
+            {
+                const cudaError_t q = cudaEventQuery(O.done);
+                if (q != cudaSuccess) { if (q == cudaErrorNotReady) cudaGetLastError(); break; }
+            }
+            close_group(O);
+            oldest++;
         }
     }
-    for (; next < n; next++)   // only after a failure: every image still gets its header verdict
     {
-        b2j_image_desc desc;
-        status[next] = b2j_parse_header(files[next], lens[next], gate, &desc);
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        consumed = ng;
     }
+    cv.notify_all();
+    for (auto &t : pool) t.join();
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream2);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
     if (rc == B2J_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail_cuda(e1 != cudaSuccess ? e1 : e2, "cudaStreamSynchronize");
-    for (Group &G : groups)
+    for (FeedGroup &G : groups)
     {
-        if (rc == B2J_OK)
-        {
-            std::vector<int32_t> st(G.count);
-            const int r2 = b2j_batch_status(G.b, ctx->stream, st.data());
-            if (r2 != B2J_OK) rc = r2;
-            else
-                for (size_t k = 0; k < G.count; k++) status[ok_idx[G.first + k]] = st[k];
-        }
-        if (G.decoded) cudaEventDestroy(G.decoded);
-        b2j_batch_destroy(G.b);
+        // after a failure the status words of the groups in flight are not trustworthy: the header verdicts stay
+        if (rc != B2J_OK) G.idx.clear();
+        close_group(G);
+        if (!G.parsed)   // only after a failure: every file still gets its header verdict
+            for (int i = G.first; i < G.first + G.count; i++) { b2j_image_desc desc; status[i] = b2j_parse_header(files[i], lens[i], gate, &desc); }
+    }
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->pin_pool.put(h_status, h_status_cap);
     }
     return rc;
+}
+
+extern "C" int b2j_decode_host_multi(b2j_ctx *const *ctxs, int n_ctx, int n, const uint8_t *const *files, const size_t *lens,
+                                     const b2j_host_opts *opts, uint8_t *const *out, int32_t *status)
+{
+    if (!ctxs || n_ctx <= 0 || n <= 0 || !files || !lens || !opts || !out || !status) return B2J_E_ARG;
+    for (int k = 0; k < n_ctx; k++) if (!ctxs[k]) return B2J_E_ARG;
+    // contiguous ranges of about equal compressed size (the decode time of an image follows its bytes)
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += lens[i];
+    std::vector<int> cut((size_t)n_ctx + 1, n);
+    cut[0] = 0;
+    {
+        size_t acc = 0;
+        int k = 1;
+        for (int i = 0; i < n && k < n_ctx; i++)
+        {
+            acc += lens[i];
+            while (k < n_ctx && acc * (size_t)n_ctx >= total * (size_t)k) cut[(size_t)k++] = i + 1;
+        }
+    }
+    std::vector<int> rcs((size_t)n_ctx, B2J_OK);
+    std::vector<std::string> errs((size_t)n_ctx);
+    std::vector<std::thread> th;
+    b2j_host_opts o = *opts;
+    if (o.n_threads <= 0) o.n_threads = std::max(1, auto_threads(0, 64) / n_ctx < 8 ? auto_threads(0, 64) / n_ctx : 8);
+    for (int k = 0; k < n_ctx; k++)
+    {
+        const int a = cut[(size_t)k], b = cut[(size_t)k + 1];
+        if (b <= a) continue;
+        th.emplace_back([&, k, a, b]() {
+            rcs[(size_t)k] = b2j_decode_host_ex(ctxs[k], b - a, files + a, lens + a, &o, out + a, status + a);
+            if (rcs[(size_t)k] != B2J_OK) errs[(size_t)k] = t_last_error;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int k = 0; k < n_ctx; k++)
+        if (rcs[(size_t)k] != B2J_OK) { t_last_error = errs[(size_t)k]; return rcs[(size_t)k]; }
+    return B2J_OK;
+}
+
+extern "C" int b2j_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return B2J_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; const int rc = fail_cuda(e, "cudaHostAlloc"); cudaGetLastError(); return rc == B2J_E_CUDA ? B2J_E_NOMEM : rc; }
+    return B2J_OK;
+}
+
+extern "C" void b2j_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int b2j_read_files(int n, const char *const *paths, int n_threads, void **arena, const uint8_t **files, size_t *lens)
+{
+    if (n <= 0 || !paths || !arena || !files || !lens) return B2J_E_ARG;
+    *arena = nullptr;
+    std::vector<size_t> off((size_t)n + 1, 0);
+    int bad = 0;
+    for (int i = 0; i < n; i++)
+    {
+        struct stat st;
+        lens[i] = 0; files[i] = nullptr;
+        if (paths[i] && stat(paths[i], &st) == 0 && S_ISREG(st.st_mode)) lens[i] = (size_t)st.st_size; else bad++;
+        off[(size_t)i + 1] = off[(size_t)i] + align_up(lens[i], 64);
+    }
+    void *base = nullptr;
+    const int rc = b2j_host_alloc(&base, off[(size_t)n] + 64);
+    if (rc != B2J_OK) return rc;
+    std::atomic<int> next(0), failed(0);
+    auto reader = [&]() {
+        for (;;)
+        {
+            const int i = next.fetch_add(1);
+            if (i >= n) return;
+            if (!lens[i]) continue;
+            uint8_t *dst = (uint8_t *)base + off[(size_t)i];
+            const int fd = open(paths[i], O_RDONLY);
+            size_t got = 0;
+            if (fd >= 0)
+            {
+                while (got < lens[i])
+                {
+                    const ssize_t r = pread(fd, dst + got, lens[i] - got, (off_t)got);
+                    if (r <= 0) break;
+                    got += (size_t)r;
+                }
+                close(fd);
+            }
+            if (got == lens[i]) files[i] = dst; else { lens[i] = 0; failed++; }
+        }
+    };
+    const int nt = std::min(auto_threads(n_threads, 16), n);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(reader);
+    for (auto &t : th) t.join();
+    *arena = base;
+    return (bad || failed.load()) ? B2J_E_ARG : B2J_OK;
+}
+
+// The reference's pixels with the default host feed.
+extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files, const size_t *lens, int gate,
+                               uint8_t *const *out_bgra, int32_t *status)
+{
+    b2j_host_opts o;
+    memset(&o, 0, sizeof(o));
+    o.gate = gate;
+    o.out_format = B2J_OUT_BGRA;
+    if (const char *ge = getenv("B2J_HOST_GROUP")) o.group = atoi(ge);
+    if (const char *te = getenv("B2J_HOST_THREADS")) o.n_threads = atoi(te);
+    return b2j_decode_host_ex(ctx, n, files, lens, &o, out_bgra, status);
 }

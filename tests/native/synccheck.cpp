@@ -14,7 +14,7 @@
 #include "b2j_internal.h"
 #include "b2j_sync.h"
 
-uint64_t g_b2j_walk_steps[4];
+uint64_t g_b2j_walk_steps[5];
 
 using namespace b2j;
 
@@ -23,11 +23,12 @@ namespace {
 struct HostLut
 {
     const uint16_t *v;
-    uint32_t ct[16];
+    WalkCtab ct[16];
     uint32_t at(uint32_t i) const { return v[i]; }
-    uint32_t at32(uint32_t i) const { return (uint32_t)v[i] | (uint32_t)v[i + 1] << 16; }
+    uint32_t tab(uint32_t off16) const { return off16; }
+    uint32_t ld(uint32_t h, uint32_t i) const { return (uint32_t)v[h + 2 * i] | (uint32_t)v[h + 2 * i + 1] << 16; }
     uint32_t hdr(int i) const { return v[i]; }
-    uint32_t ctab(uint32_t c) const { return ct[c]; }
+    WalkCtab ctab(uint32_t c) const { return ct[c]; }
 };
 
 struct HostWalk
@@ -35,8 +36,8 @@ struct HostWalk
     StreamWords stream;
     HostLut lut;
     uint32_t tot, ny, nu;
-    void init() { for (uint32_t c = 0; c < tot && c < 16; c++) lut.ct[c] = walk_ctab_entry(lut, c, ny, nu); }
-    WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit, tot); }
+    void init() { for (uint32_t c = 0; c < tot && c < 16; c++) lut.ct[c] = walk_ctab_entry(lut, c, ny, nu, tot); }
+    WalkResult walk(WalkState s, uint32_t limit) const { return walk_stream(stream, lut, s, limit); }
 };
 
 // ---- the independent check: canonical codes matched bit by bit, one symbol per step ----------------------------
@@ -97,7 +98,12 @@ WalkResult ref_walk(const RefImage &im, const PlainBits &b, WalkState s, uint32_
         if (z == 0)
         {
             const int sym = canon_symbol(im.dc[comp], b, p, &len);
-            if (sym < 0 || sym > 16) { bad = true; break; }
+            if (sym < 0 || sym > 16)
+            {
+                if (r.nblk == 0) { r.fs = p; r.fc = c; }
+                r.nblk++;   // counted as started (the decode lane flags it)
+                bad = true; break;
+            }
             const uint32_t v = sym ? b.bits(p + len, sym) : 0u;
             const int32_t diff = sym == 0 ? 0 : ((v >> (sym - 1)) ? (int32_t)v : (int32_t)v + 1 - (1 << sym));   // decoder.cpp:72-82
             if (getenv("B2J_SYNCCHECK_TRACE")) fprintf(stderr, "  ref dc p %u len %d sym %d diff %d comp %u\n", p, len, sym, diff, comp);
@@ -140,7 +146,7 @@ extern "C" {
 int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, uint64_t *stats)
 {
     memset(stats, 0, 10 * sizeof(uint64_t));
-    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = g_b2j_walk_steps[2] = g_b2j_walk_steps[3] = 0;
+    g_b2j_walk_steps[0] = g_b2j_walk_steps[1] = g_b2j_walk_steps[2] = g_b2j_walk_steps[3] = g_b2j_walk_steps[4] = 0;
     b2j_image_desc d;
     int rc = b2j_parse_header(file, len, gate, &d);
     if (rc != B2J_OK) return -100 + rc;
@@ -251,12 +257,14 @@ int b2j_synccheck(const uint8_t *file, size_t len, int gate, int force_sweep, ui
     };
     for (uint32_t k = 0; k < n_chunks; k++)
         if (!run_chunk(k, false, make_uint2(0, 0))) { delete sh; return -5; }
-    // the sweep: in order, re-run what started from a state its predecessor did not end in
+    // the sweep: in order, repair what started from a state its predecessor did not end in (sync_repair_chunk, as the kernel)
     for (uint32_t k = 1; k < n_chunks; k++)
         if (chunk_entry[k].x != chunk_exit[k - 1].x || chunk_entry[k].y != chunk_exit[k - 1].y)
         {
             stats[5]++;
-            if (!run_chunk(k, true, chunk_exit[k - 1])) { delete sh; return -5; }
+            uint32_t t4[4] = {0, 0, 0, 0};
+            sync_repair_chunk(w, k, n_sub, bits, recs.data(), chunk_exit[k - 1], t4, chunk_exit[k]);
+            chunk_entry[k] = chunk_exit[k - 1];
         }
     delete sh;
     int bad = 0;

@@ -22,21 +22,21 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(L, name), "missing export " + name
     assert sorted(declared) == sorted(b2j.EXPORTED_SYMBOLS)
-    assert L.b2j_abi_version() == 2
+    assert L.b2j_abi_version() == 3
 
 
 def test_struct_sizes_match_header(built):
     import subprocess
     import tempfile
     import ocljpegdecoder_b200 as b2j
-    code = '#include "b2j.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu", sizeof(b2j_image_desc), sizeof(b2j_batch_info), sizeof(b2j_stage_times));return 0;}'
+    code = '#include "b2j.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu", sizeof(b2j_image_desc), sizeof(b2j_batch_info), sizeof(b2j_stage_times), sizeof(b2j_host_opts));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         with open(c, "w") as f:
             f.write(code)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
         out = subprocess.check_output([os.path.join(d, "s")]).decode().split()
-    assert [int(x) for x in out] == [ctypes.sizeof(b2j.ImageDesc), ctypes.sizeof(b2j.BatchInfo), ctypes.sizeof(b2j.StageTimes)]
+    assert [int(x) for x in out] == [ctypes.sizeof(b2j.ImageDesc), ctypes.sizeof(b2j.BatchInfo), ctypes.sizeof(b2j.StageTimes), ctypes.sizeof(b2j.HostOpts)]
 
 
 def test_parse_header_agrees_with_oracle(built, oracle, fixture_jpeg):

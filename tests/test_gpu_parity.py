@@ -422,11 +422,10 @@ def test_robust_mode_decodes_files_with_comments(decoder, oracle):
     _check_pixels(outs[1], bgra)
 
 
-def test_kernel_variants_agree(decoder):
-    """The kernel variants kept for measurement -- three-kernel pre-pass (B2J_PREPASS=3) and the Huffman decoder
-    fed through per-lane cp.async rings (B2J_HUFF_VARIANT=1) -- must produce the same planes, pixels and status
-    words as the defaults: many chunks per image (several look-back windows), streams that end in the middle of
-    a chunk (dead chunks behind), no restart markers, broken restart numbering, dense q100 blocks (ring underflow)."""
+def test_prepass_and_reader_stress_batch(decoder, oracle):
+    """Inputs that stress the single-pass pre-pass and the bit readers, against the oracle: many chunks per image
+    (several look-back windows), a stream that ends in the middle of a chunk (dead chunks behind), no restart markers,
+    broken restart numbering, stuffed bytes at chunk borders, dense q100 blocks with optimised tables."""
     good = synth.synth_jpeg(320, 240, 5, 90, "420", 4)
     b = bytearray(good)
     k = good.index(b"\xff\xd1")
@@ -436,22 +435,20 @@ def test_kernel_variants_agree(decoder):
              synth.synth_jpeg(640, 480, 93, 75, "420", 0), _crafted((2, 2), 80, 48, 2, 3, seed=3, stuffed=True),
              synth.synth_jpeg(800, 608, 94, 100, "420", 3, optimize=True)]
     assert (len(big) + 16383) // 16384 > 64
-    res = {}
-    for name, env in (("default", {}), ("prepass3", {"B2J_PREPASS": "3"}), ("ring", {"B2J_HUFF_VARIANT": "1"})):
-        os.environ.update(env)
-        try:
-            res[name] = _decode(decoder, files)
-        finally:
-            for key in env:
-                del os.environ[key]
-    st0, c0, p0 = res["default"]
-    assert st0[0] == 0 and st0[1] == 0 and st0[3] != 0 and st0[4] != 0 and st0[7] == 0
-    for name in ("prepass3", "ring"):
-        st, c, p = res[name]
-        assert st.tolist() == st0.tolist(), name
-        for i in range(len(files)):
-            assert np.array_equal(c[i], c0[i]), (name, i)
-            assert np.array_equal(p[i], p0[i]), (name, i)
+    st, coefs, pix = _decode(decoder, files)
+    assert st[0] == 0 and st[1] == 0 and st[3] != 0 and st[4] != 0 and st[7] == 0
+    st2, coefs2, pix2 = _decode(decoder, files)
+    assert st2.tolist() == st.tolist()
+    oracle.set_strict(False)
+    try:
+        for i in (0, 1, 2, 5, 6, 7):
+            rc, _, coef, bgra = oracle.decode(files[i])
+            assert rc == 0, i
+            assert np.array_equal(coefs[i], coef), i
+            _check_pixels(pix[i], bgra)
+            assert np.array_equal(pix2[i], pix[i])
+    finally:
+        oracle.set_strict(True)
 
 
 def test_output_formats(decoder, oracle):
@@ -627,3 +624,84 @@ def test_dc_category_above_16_is_flagged(decoder, oracle):
     st, _, _ = _decode(decoder, [data, good])
     assert st[1] == 0
     assert st[0] & 0x01, "DC category 17 must be flagged as B2J_ST_BAD_CODE, status %#x" % st[0]
+
+
+def test_decode_host_ex_formats_threads_and_groups(decoder, oracle):
+    """b2j_decode_host_ex: every output layout, 1 and several host threads, small groups (buffers of finished groups are
+    recycled while later groups are still being staged), a refused file in the middle. All against the oracle."""
+    import ocljpegdecoder_b200 as b2j
+    specs = [(320, 240, "420", 90, 8), (200, 120, "444", 85, 0), (131, 77, "420", 75, 3), (322, 98, "422", 60, 0), (65, 33, "444", 95, 0),
+             (500, 375, "420", 75, 0), (96, 64, "444", 80, 2)]
+    files = [synth.synth_jpeg(w, h, 900 + i, q, ss, ri) for i, (w, h, ss, q, ri) in enumerate(specs)] * 5
+    files.insert(9, b"\xff\xd8 this is not a jpeg")
+    want = {}
+    oracle.set_strict(False)
+    try:
+        for i, f in enumerate(files):
+            if i == 9:
+                continue
+            key = hashlib.sha256(f).hexdigest()
+            if key not in want:
+                rc, _, _, bgra = oracle.decode(f, 1)
+                assert rc == 0
+                want[key] = bgra
+    finally:
+        oracle.set_strict(True)
+    for fmt, nt, group in [(b2j.OUT_BGRA, 1, 4), (b2j.OUT_RGB24, 4, 3), (b2j.OUT_RGB_PLANAR, 3, 0), (b2j.OUT_BGRA, 0, 0)]:
+        outs, st = decoder.decode_host_ex(files, out_format=fmt, n_threads=nt, group=group)
+        assert st[9] < 0 and not np.delete(st, 9).any(), st
+        for i, f in enumerate(files):
+            if i == 9:
+                continue
+            ref = want[hashlib.sha256(f).hexdigest()]
+            if fmt == b2j.OUT_BGRA:
+                assert np.array_equal(outs[i], ref), (fmt, i)
+            elif fmt == b2j.OUT_RGB24:
+                assert np.array_equal(outs[i], ref[..., 2::-1]), (fmt, i)
+            else:
+                assert np.array_equal(outs[i], np.moveaxis(ref[..., 2::-1], 2, 0)), (fmt, i)
+    # the plain call is the same path with the defaults
+    outs, st = decoder.decode_host(files)
+    assert st[9] < 0 and not np.delete(st, 9).any()
+    assert np.array_equal(outs[0], want[hashlib.sha256(files[0]).hexdigest()])
+
+
+def test_decode_host_multi_and_pinned_buffers(decoder, oracle, tmp_path):
+    """b2j_decode_host_multi shards one list of files over several contexts (one host thread each; here as many contexts
+    as the box has GPUs, at least two -- two contexts on one GPU exercise the same threading), reading the files with
+    b2j_read_files into a pinned arena and writing RGB24 into one pinned output buffer (b2j_host_alloc)."""
+    import ocljpegdecoder_b200 as b2j
+    files = [synth.synth_jpeg(160 + 16 * (i % 5), 120 + 8 * (i % 3), 300 + i, 70 + i % 25, ["420", "444", "422"][i % 3], [0, 4][i % 2]) for i in range(23)]
+    paths = []
+    for i, f in enumerate(files):
+        p = tmp_path / ("f%02d.jpg" % i)
+        p.write_bytes(f)
+        paths.append(str(p))
+    rc, arena, addrs, lens = b2j.read_files(paths, 3)
+    assert rc == 0 and lens == [len(f) for f in files]
+    rc_bad, arena2, addrs2, lens2 = b2j.read_files(paths[:2] + [str(tmp_path / "missing.jpg")], 2)
+    assert rc_bad != 0 and addrs2[2] is None and lens2[:2] == lens[:2]
+    b2j.host_free(arena2)
+    descs = [b2j.parse_header(f)[1] for f in files]
+    sizes = [d.width * d.height * 3 for d in descs]
+    offs = np.concatenate([[0], np.cumsum([(s + 255) // 256 * 256 for s in sizes])])
+    pinned = b2j.PinnedBuffer(int(offs[-1]))
+    ngpu = max(2, min(8, decoder.lib.b2j_device_count()))
+    decs = [decoder] + [b2j.Decoder(k % decoder.lib.b2j_device_count()) for k in range(1, ngpu)]
+    try:
+        outs, st = b2j.decode_host_multi(decs, addrs, lens=lens, outs=[pinned.address + int(o) for o in offs[:-1]], out_format=b2j.OUT_RGB24, n_threads=2, group=4)
+        assert not st.any(), st
+        oracle.set_strict(False)
+        try:
+            for i in range(0, len(files), 3):
+                rc, _, _, bgra = oracle.decode(files[i], 1)
+                assert rc == 0
+                got = pinned.array[int(offs[i]):int(offs[i]) + sizes[i]].reshape(descs[i].height, descs[i].width, 3)
+                assert np.array_equal(got, bgra[..., 2::-1]), i
+        finally:
+            oracle.set_strict(True)
+    finally:
+        for d in decs[1:]:
+            d.close()
+        pinned.close()
+        b2j.host_free(arena)
