@@ -650,8 +650,50 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
             if (seg + 1 == n_sub && pre.blk + rec.nblk < im.blk_count) err |= B2J_ST_OVERRUN;   // the stream ends before the last block
             end = clean_len[cta.img];
         }
-        start = start_bit >> 3;
         decodable = active && nblk > 0;
+        // Lanes change places: sorted by the phase of their first block inside the MCU, then by falling block count.
+        // The decode loop below runs block by block in warp lockstep, so a warp costs (longest lane in blocks) x
+        // (longest block of every round): lanes of one phase meet the same component in every round, and neighbours
+        // in block count finish together. Counting sort over 640 keys in the (still zero) slot area.
+        {
+            uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_slots);      // [640] counters, then their exclusive prefix
+            uint32_t *s_wsum = s_hist + 640;                               // [4] warp totals of the scan
+            uint32_t *s_desc = s_hist + 648;                               // [kHuffThreads][6] work descriptors
+            const uint32_t key = decodable ? bi * 64u + (63u - min(nblk, 63u)) : 639u;
+            const uint32_t within = atomicAdd(&s_hist[key], 1u);
+            __syncthreads();
+            uint32_t h[5], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { h[k] = s_hist[tid * 5u + k]; sum += h[k]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += t;
+            }
+            if (lane == 31u) s_wsum[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int w = 0; w < kHuffThreads / 32; w++) run += (w < (int)(tid >> 5)) ? s_wsum[w] : 0u;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { s_hist[tid * 5u + k] = run; run += h[k]; }
+            __syncthreads();
+            uint32_t *d = s_desc + (s_hist[key] + within) * 6u;
+            d[0] = nblk | bi << 16; d[1] = blk0; d[2] = start_bit; d[3] = (uint32_t)dc0; d[4] = (uint32_t)dc1; d[5] = (uint32_t)dc2;
+            __syncthreads();
+            const uint32_t *m = s_desc + tid * 6u;
+            nblk = m[0] & 0xFFFFu; bi = m[0] >> 16; blk0 = m[1]; start_bit = m[2];
+            dc0 = (int32_t)m[3]; dc1 = (int32_t)m[4]; dc2 = (int32_t)m[5];
+            decodable = nblk > 0;
+            end = bits >> 3;   // every lane may hold work now, whatever its own sub-sequence was
+            __syncthreads();
+            uint4 *z = reinterpret_cast<uint4 *>(s_slots);
+            for (uint32_t k = tid; k < (648u + kHuffThreads * 6u + 3u) / 4u; k += kHuffThreads) z[k] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+        }
+        start = start_bit >> 3;
     }
 
     BitReader<1> br;

@@ -224,32 +224,34 @@ def test_decode_host_api(decoder, oracle, fixture_jpeg):
 
 
 def test_full_size_config2_batch(decoder, oracle):
-    """BASELINE configs[1] at full size: 256 x 1080p 4:2:0 q90 RI=16. Exact comparison on a sample;
-    for the whole batch: clean status, idempotence of the pixel checksum, and the checksum of every
-    image decoded in the big batch equals the checksum of the same image decoded in a small batch."""
+    """BASELINE configs[1] at full size: 256 x 1080p 4:2:0 q90 RI=16. EVERY image of the batch: coefficients (the
+    reference's int32 tap) and pixels against the unmodified reference where it decodes the file, else against the
+    non-strict oracle port (SHA-256 per image, computed on a pool of host processes); clean status, idempotence of
+    the pixel checksum, and big-batch == small-batch."""
+    import cpu_digests
     files = synth.config_batch(1, 256)
     batch = decoder.batch(files)
     batch.upload()
     batch.decode()
     assert not batch.status().any()
-    sums = [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in range(0, 256, 5)]
+    want = cpu_digests.config_digests(1, range(256))
+    kinds = [w[0] for w in want]
+    assert "failed" not in kinds
+    print("256 x 1080p: %d images against the unmodified reference, %d against the oracle port" % (kinds.count("reference"), kinds.count("oracle")))
+    sums = []
+    for i in range(256):
+        hc = hashlib.sha256(batch.coefs(i).tobytes()).hexdigest()
+        hp = hashlib.sha256(batch.pixels(i).tobytes()).hexdigest()
+        assert hc == want[i][1], "coefficients of image %d differ from the %s" % (i, want[i][0])
+        assert hp == want[i][2], "pixels of image %d differ from the %s" % (i, want[i][0])
+        sums.append(hp)
     batch.decode_steps(2)
-    sums2 = [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in range(0, 256, 5)]
-    assert sums == sums2
-    oracle.set_strict(False)
-    try:
-        for i in (0, 37, 101, 255):
-            rc, _, coef, bgra = oracle.decode(files[i])
-            assert rc == 0
-            assert np.array_equal(batch.coefs(i), coef)
-            _check_pixels(batch.pixels(i), bgra)
-    finally:
-        oracle.set_strict(True)
+    assert [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in range(0, 256, 5)] == sums[::5]
     batch.close()
     st, _, pix = _decode(decoder, [files[k] for k in (10, 250)])
     assert not st.any()
-    assert hashlib.sha256(pix[0].tobytes()).hexdigest() == sums[2]
-    assert hashlib.sha256(pix[1].tobytes()).hexdigest() == sums[50]
+    assert hashlib.sha256(pix[0].tobytes()).hexdigest() == sums[10]
+    assert hashlib.sha256(pix[1].tobytes()).hexdigest() == sums[250]
 
 
 @pytest.mark.parametrize("cfg,count", [(2, 2), (3, 1), (4, 64)])
@@ -269,7 +271,7 @@ def test_other_baseline_configs(decoder, oracle, cfg, count):
         oracle.set_strict(True)
 
 
-@pytest.mark.parametrize("cfg,count,stride", [(2, 64, 7), (4, 8192, 61)])
+@pytest.mark.parametrize("cfg,count,stride", [(2, 64, 7), (4, 8192, 10)])
 def test_full_size_selfsync_configs(decoder, oracle, cfg, count, stride):
     """BASELINE configs[2] and configs[4] at full size (64 x 4K 4:4:4 q95, 8192 x 500x375 4:2:0 q75; no restart
     markers: the self-synchronising path). Whole batch: clean status; on every `stride`-th image: the pixel
@@ -287,15 +289,13 @@ def test_full_size_selfsync_configs(decoder, oracle, cfg, count, stride):
     batch.decode_steps(2)
     assert not batch.status().any()
     assert sums == [hashlib.sha256(batch.pixels(i).tobytes()).hexdigest() for i in idx]
-    oracle.set_strict(False)
-    try:
-        for i in (0, idx[len(idx) // 2], count - 1):
-            rc, _, coef, bgra = oracle.decode(files[i])
-            assert rc == 0
-            assert np.array_equal(batch.coefs(i), coef)
-            _check_pixels(batch.pixels(i), bgra)
-    finally:
-        oracle.set_strict(True)
+    # every `stride`-th image (>= 10 % of the batch) against the reference / the oracle port, coefficients and pixels
+    import cpu_digests
+    want = cpu_digests.config_digests(cfg, idx)
+    for i, w, hp in zip(idx, want, sums):
+        assert w[0] != "failed"
+        assert hashlib.sha256(batch.coefs(i).tobytes()).hexdigest() == w[1], (cfg, i, w[0])
+        assert hp == w[2], (cfg, i, w[0])
     batch.close()
     some = idx[::max(1, len(idx) // 6)]
     st, _, pix = _decode(decoder, [files[k] for k in some])
