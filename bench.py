@@ -157,6 +157,14 @@ def usable_for_cpu(pool, idx):
     return good, len(idx) - len(good)
 
 
+def cpu_sample_size(cfg, n_files):
+    """How many files of the batch one CPU pass decodes -- the same in the reference arm and in the cpu_baseline leg:
+    the whole 256-image batch of config 1, about 1.2 GPix (a second or two on 16 cores) of the larger ones."""
+    import synth
+    npix = synth.CONFIGS[cfg]["width"] * synth.CONFIGS[cfg]["height"]
+    return n_files if cfg == 1 else max(1, min(n_files, int(1.2e9 // npix)))
+
+
 def build_oracle_only():
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], stdout=sys.stderr)
@@ -171,10 +179,9 @@ def reference_arm(args, rank, world):
     build_oracle_only()          # the checker only: libb2j.so is neither built nor loaded by this arm
     w = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
-    budget_pix = 1.2e9 if args.config != 1 else 1e12     # per step, about a second of work on 16 cores
     files = synth.config_batch(args.config, w["count"])
     npix = synth.CONFIGS[args.config]["width"] * synth.CONFIGS[args.config]["height"]
-    take = max(1, min(len(files), int(budget_pix // npix)))
+    take = cpu_sample_size(args.config, len(files))
     pool = CpuPool(files, cores, skip_gate=(args.config == 3))
     good, bad = usable_for_cpu(pool, list(range(take)))
     for _ in range(args.warmup):
@@ -407,13 +414,13 @@ def main():
         pool = CpuPool(files, pool_cores, skip_gate=(cfg == 3))
         if rank == 0 and world == 1:
             npix = synth.CONFIGS[cfg]["width"] * synth.CONFIGS[cfg]["height"]
-            n_cpu = args.cpu_sample or max(1, min(len(files), cores * 8, int(0.6e9 // npix) or 1))
+            n_cpu = args.cpu_sample or cpu_sample_size(cfg, len(files))
             good, bad = usable_for_cpu(pool, list(range(n_cpu)))        # also warms the workers
-            mp_all, dt_all, res = pool.decode(good)
+            mp_all, dt_all, res = max((pool.decode(good) for _ in range(2)), key=lambda r: r[0])   # the better of two passes
             th, tm = sum(r[1] for r in res), sum(r[2] for r in res)
             cpu = {"value": round(mp_all, 3), "unit": "MPix/s", "cores": cores, "kind": cpu_kind(),
-                   "sample": "%d of the %d images, one process per host core, %.2f s wall; the reference aborts on %d of the first %d "
-                             "(lost RSTn at a 2 KiB read boundary), those are excluded" % (len(good), len(files), dt_all, bad, n_cpu),
+                   "sample": "%d of the %d images (the sample of the reference arm), one process per host core, better of two passes, %.2f s wall; "
+                             "the reference aborts on %d of the first %d (lost RSTn at a 2 KiB read boundary), those are excluded" % (len(good), len(files), dt_all, bad, n_cpu),
                    "one_core_mpix_s": round(len(good) * npix / (th + tm) / 1e6, 3) if (th + tm) > 0 else None,
                    "stage_timer_mpix_s": round(len(good) * npix / (th + tm) * cores / 1e6, 3) if (th + tm) > 0 else None,
                    "huffman_share": round(th / (th + tm), 3) if (th + tm) > 0 else None}

@@ -1,18 +1,27 @@
-"""Probe (not a pytest file): b2j_decode_host wall time for several group sizes, with and without the ramp."""
+"""Probe (not a pytest file): b2j_decode_host_ex wall time for several group sizes and host-thread counts.
+usage: python tests/e2e_probe.py config n_images"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+import numpy as np
 import ocljpegdecoder_b200 as b2j, synth
-files = synth.config_batch(1, 256)
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+files = synth.config_batch(cfg, n)
+c = synth.CONFIGS[cfg]
+npix = c["width"] * c["height"]
 dec = b2j.Decoder(0)
-outs_t = [torch.empty((1080, 1920, 4), dtype=torch.uint8, pin_memory=True) for _ in range(256)]
-outs = [o.numpy() for o in outs_t]
-for ramp in ("0", "1"):
-    for group in ("8", "16", "32", "64"):
-        os.environ["B2J_HOST_RAMP"] = ramp
-        os.environ["B2J_HOST_GROUP"] = group
+pinned = b2j.PinnedBuffer(n * npix * 4)
+outs = [pinned.address + i * npix * 4 for i in range(n)]
+print("config %d, %d images, %d host cores; PCIe floor of the BGRA download at 56 GB/s: %.1f ms" % (cfg, n, os.cpu_count(), n * npix * 4 / 56e9 * 1e3))
+for threads in (1, 2, 4, 8, 16):
+    for group in (16, 32, 64, 128, 256):
         ts = []
-        for rep in range(6):
-            t0 = time.perf_counter(); dec.decode_host(files, outs); ts.append(1e3 * (time.perf_counter() - t0))
-        print("ramp %s group %2s: min %.2f ms  median %.2f ms" % (ramp, group, min(ts[1:]), sorted(ts[1:])[2]), flush=True)
+        for rep in range(4):
+            t0 = time.perf_counter()
+            _, st = dec.decode_host_ex(files, outs=outs, n_threads=threads, group=group)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        assert not st.any()
+        print("threads %2d group %3d: min %.2f ms  median %.2f ms" % (threads, group, min(ts[1:]), sorted(ts[1:])[1]), flush=True)
+dec.close()
+pinned.close()

@@ -660,6 +660,21 @@ def test_decode_host_ex_formats_threads_and_groups(decoder, oracle):
                 assert np.array_equal(outs[i], ref[..., 2::-1]), (fmt, i)
             else:
                 assert np.array_equal(outs[i], np.moveaxis(ref[..., 2::-1], 2, 0)), (fmt, i)
+    # caller buffers that are neighbours in memory: the downloads of neighbouring images merge into one copy
+    good = [f for i, f in enumerate(files) if i != 9]
+    descs = [b2j.parse_header(f)[1] for f in good]
+    for fmt, bpp in ((b2j.OUT_BGRA, 4), (b2j.OUT_RGB24, 3)):
+        sizes = [d.width * d.height * bpp for d in descs]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        big = np.zeros(int(offs[-1]) + 16, np.uint8)
+        base = big.ctypes.data
+        _, st = decoder.decode_host_ex(good, outs=[base + int(o) for o in offs[:-1]], out_format=fmt, n_threads=2, group=8)
+        assert not st.any()
+        assert not big[int(offs[-1]):].any()
+        for i, f in enumerate(good):
+            ref = want[hashlib.sha256(f).hexdigest()]
+            got = big[int(offs[i]):int(offs[i + 1])].reshape(descs[i].height, descs[i].width, bpp)
+            assert np.array_equal(got, ref if bpp == 4 else ref[..., 2::-1]), (fmt, i)
     # the plain call is the same path with the defaults
     outs, st = decoder.decode_host(files)
     assert st[9] < 0 and not np.delete(st, 9).any()
