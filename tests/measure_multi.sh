@@ -20,7 +20,7 @@ for g in $NS; do if [ $g != 1 ]; then run 4 $g 10; run 3 $g 30; fi; done
 } > $o/${tag}_d2h_probe_${NG}gpu.txt 2>&1
 python tests/multi_probe.py 1 $((64*NG)) 2 > $o/${tag}_multi_cabi_cfg1_${NG}gpu.txt 2>&1
 python tests/multi_probe.py 4 4096 2 > $o/${tag}_multi_cabi_cfg4_${NG}gpu.txt 2>&1
-python -m pytest tests/test_gpu_parity.py -q -k "multi" > $o/${tag}_pytest_multi_${NG}gpu.log 2>&1
+python -m pytest tests/test_gpu_parity.py -q -k "multi or host_ex or decode_host_api" > $o/${tag}_pytest_multi_${NG}gpu.log 2>&1
 grep -h '"metric"' $o/${tag}_bench_cfg*_n*.json | python -c "
 import sys, json
 for l in sys.stdin:
