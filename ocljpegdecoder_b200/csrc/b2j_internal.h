@@ -36,7 +36,11 @@ constexpr int kLutMaxEntries = 32768;    // u16 entries of a whole LUT set, walk
 #ifndef B2J_WALK_BITS
 #define B2J_WALK_BITS 10
 #endif
-constexpr int kWalkBits = B2J_WALK_BITS; // index width of the walk tables, DC and AC alike (several AC symbols per lookup)
+constexpr int kWalkBits = B2J_WALK_BITS; // index width of the AC walk tables (several AC symbols per lookup)
+#ifndef B2J_WALK_BITS_DC
+#define B2J_WALK_BITS_DC 8
+#endif
+constexpr int kWalkBitsDc = B2J_WALK_BITS_DC;   // index width of the DC walk tables: small, shared memory decides how many CTAs an SM holds
 constexpr int kTileBlocks = 192;         // 8x8 blocks per IDCT/colour tile (= threads per CTA)
 constexpr uint32_t kSegInvalid = 0xFFFFFFFFu;
 constexpr uint32_t kChunkDead = 0xFFFFFFFFu;
@@ -52,7 +56,7 @@ constexpr uint32_t kNoTerm = 0xFFFFu;
 //             offset relative to the end of the primary table, in units of kLutSubAlign entries
 //   invalid : 0 (no codeword has this prefix)
 // Walk tables, used by the walks of the self-synchronising path only (they need no coefficient values): 32-bit
-// entries indexed by the next kWalkBits bits, two 16-bit halves of one layout:
+// entries indexed by the next kWalkBits (AC) / kWalkBitsDc (DC) bits, two 16-bit halves of one layout:
 //          bits 0-4  bits consumed (codes + value bits, <= 31)
 //          bit  7    the set ends with the end-of-block symbol
 //          bits 8-15 scan positions needed: sum of run + 1, plus 1 for a closing end-of-block symbol (the block must

@@ -239,7 +239,7 @@ B2J_HD WalkResult walk_stream(const StreamWords &stream, const LUT &lut, WalkSta
         {
             const uint32_t pk = fsh_l(nxt, cur, p);
             const bool dc = z == 0u;
-            uint32_t e = lut.ld(tb, pk >> (32u - (uint32_t)kWalkBits));
+            uint32_t e = lut.ld(tb, pk >> (dc ? 32u - (uint32_t)kWalkBitsDc : 32u - (uint32_t)kWalkBits));
             // the whole group where it fits, else its first symbol (a DC entry is one symbol, its high half the difference)
             const bool whole = dc || z + byte1(e) - alone_lo >= alone_span;
             const int32_t diff = (int32_t)e >> 16;

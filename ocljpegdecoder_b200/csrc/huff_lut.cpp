@@ -90,7 +90,7 @@ bool build_huff_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc
 
 bool build_walk_lut(const uint8_t counts[16], const uint8_t *symbols, bool is_dc, std::vector<uint16_t> &out)
 {
-    const int K = kWalkBits;
+    const int K = is_dc ? kWalkBitsDc : kWalkBits;
     struct Code { uint32_t code; int len; int sym; };
     Code codes[256];
     int n = 0;
