@@ -118,7 +118,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_clean_end, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states;
+    size_t off_clean, off_clean_end, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states, off_zero_end;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -519,12 +519,14 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     b->off_clean_end = off;
     b->off_clean_len = place(4 * (size_t)n);
     b->off_seg_start = place(4 * (size_t)seg_total);
-    b->off_status = place(4 * (size_t)n);
     b->off_recs = place(sizeof(SubRec) * (size_t)sub_total);
     b->off_pres = place(sizeof(uint4) * (sctas.size() + 1));
-    b->off_sync_stats = place(4 * 8);
     b->off_chunk_states = place(sizeof(uint4) * (sctas.size() + 1));
+    // what every decode starts from zero, side by side: one memset
+    b->off_status = place(4 * (size_t)n);
+    b->off_sync_stats = place(4 * 8);
     b->off_chunk_state = place(8 * chunk_img.size());
+    b->off_zero_end = off;
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
     b->coef_rows = blk_total + kTileBlocks;   // one tile of padding: the last tile may read past the last block
@@ -673,10 +675,8 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
     const DecodeArgs &a = b->args;
     cudaStream_t s2 = b->ctx->stream2;
     if (ev) CU_TRY(cudaEventRecord(ev[0], s));
-    CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));
-    CU_TRY(cudaMemsetAsync(a.status, 0, 4 * (size_t)b->n, s));
-    CU_TRY(cudaMemsetAsync(a.sync_stats, 0, 4 * 8, s));
-    CU_TRY(cudaMemsetAsync(a.chunk_state, 0, 8 * (size_t)a.n_chunks, s));
+    if (a.n_huff_ctas) CU_TRY(cudaMemsetAsync(a.seg_start, 0xFF, 4 * (size_t)b->n_segs_total, s));   // read by the restart-interval decoder only
+    CU_TRY(cudaMemsetAsync(b->d_scratch + b->off_status, 0, b->off_zero_end - b->off_status, s));   // status words, sync stats, look-back words
     const size_t np = b->parts.size();
     for (size_t p = 0; p < np; p++)
     {
