@@ -161,6 +161,20 @@ def _host_call_args(files, outs, gate, fmt):
     return outs, fp, (ctypes.c_void_p * n)(*[o if isinstance(o, int) else o.ctypes.data for o in outs])
 
 
+class HostArgs:
+    """The argument arrays of a b2j_decode_host* call, marshalled once (8192 small files cost tens of milliseconds of
+    ctypes work per call otherwise): files / lens / outs as for Decoder.decode_host_ex."""
+
+    def __init__(self, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0):
+        self.n = len(files)
+        self.files = files                      # keeps the bytes objects alive
+        lens = lens if lens is not None else [len(f) for f in files]
+        self.outs, self.fp, self.op = _host_call_args(files, outs, gate, out_format)
+        self.ln = (ctypes.c_size_t * self.n)(*lens)
+        self.opts = HostOpts(gate=gate, out_format=out_format, n_threads=n_threads, group=group)
+        self.status = np.zeros(self.n, np.int32)
+
+
 class PinnedBuffer:
     """b2j_host_alloc / b2j_host_free: page-locked host memory, viewed as a numpy uint8 array."""
 
@@ -261,6 +275,12 @@ class Decoder:
         _check(self.lib.b2j_decode_host(self._h, n, fp, ln, gate, op, status.ctypes.data), "b2j_decode_host")
         return outs, status
 
+
+    def decode_host_args(self, args):
+        """b2j_decode_host_ex with arguments marshalled beforehand (HostArgs). Returns (outs, status)."""
+        _check(self.lib.b2j_decode_host_ex(self._h, args.n, args.fp, args.ln, ctypes.byref(args.opts), args.op, args.status.ctypes.data),
+               "b2j_decode_host_ex")
+        return args.outs, args.status
 
     def decode_host_ex(self, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0):
         """b2j_decode_host_ex: like decode_host with an output layout and host threads. files: bytes objects or addresses
