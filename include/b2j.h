@@ -75,7 +75,7 @@ extern "C" {
 /* ---- accept gate ---- */
 #define B2J_GATE_REFERENCE 0 /* exactly decoder.cpp:58-69: 4:2:0 (22,11,11) and 4:4:4        */
 #define B2J_GATE_EXTENDED 1  /* + every luma sampling h x v (1..4) whose chroma factors divide it, <= 10 blocks per MCU:
-                              * 4:2:2 (21,11,11; BASELINE config 4), 4:4:0 (12), 4:1:1 (41), 14, 31, 42, ... -- the
+                              * 4:2:2 (21,11,11; BASELINE configs[3]), 4:4:0 (12), 4:1:1 (41), 14, 31, 42, ... -- the
                               * reference's CPU loops decode these as they are (decoder.cpp:429-495), only its gate
                               * refuses them -- and, beyond the reference ("only works in ?:1:1 mode", decoder.cpp:455),
                               * chroma components with several blocks per MCU (22,21,21): the same pixel replication */
