@@ -15,8 +15,10 @@ constexpr int kScanGroups = 4;           // 16-byte groups per thread in the pre
 constexpr int kScanThreads = 256;
 constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of raw scan one CTA of the pre-pass handles
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
-constexpr int kSubBytes = 128;           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
-constexpr int kSyncRounds = 6;           // parallel synchronisation rounds before the sequential sweep
+#ifndef B2J_SUB_BYTES
+#define B2J_SUB_BYTES 128
+#endif
+constexpr int kSubBytes = B2J_SUB_BYTES; // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each); 64 and 32 were measured slower           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
 #ifndef B2J_SYNC_PRE_LANES
 #define B2J_SYNC_PRE_LANES 2
 #endif
