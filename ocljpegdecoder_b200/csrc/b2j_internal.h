@@ -18,7 +18,7 @@ constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffma
 #ifndef B2J_SUB_BYTES
 #define B2J_SUB_BYTES 128
 #endif
-constexpr int kSubBytes = B2J_SUB_BYTES; // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each); 64 and 32 were measured slower           // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each)
+constexpr int kSubBytes = B2J_SUB_BYTES; // self-synchronising decode: bytes of clean stream per sub-sequence (one lane each); 64 and 32 were measured slower
 #ifndef B2J_SYNC_PRE_LANES
 #define B2J_SYNC_PRE_LANES 2
 #endif
