@@ -24,7 +24,8 @@
 // A chunk's result is right if the entry state of its first lane is right. For the first chunk of an image that is
 // the true start state; for every other chunk it is the exit state of its pre-lanes, i.e. right unless the guess
 // failed to fall into step within kSyncPre sub-sequences. k_sync_sweep compares every chunk's assumed entry with its
-// predecessor's exit and re-runs the (rare) chunks that disagree, in order, with the entry forced: correctness never
+// predecessor's exit and repairs the (rare) chunks that disagree, in order: their sub-sequences are walked again from
+// the true entry state until a walk falls into step with the old records (sync_repair_chunk): correctness never
 // depends on luck.
 #ifndef B2J_SYNC_H_INCLUDED
 #define B2J_SYNC_H_INCLUDED

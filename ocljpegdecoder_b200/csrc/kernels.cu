@@ -818,7 +818,8 @@ k_huff_decode(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 //   k_sync_chunks   one CTA per chunk of kSyncLanes sub-sequences: round 0 and all further rounds of the chunk in
 //                   shared memory (b2j_sync.h), records + chunk totals + chunk entry/exit state out;
 //   k_sync_sweep    one CTA per image: every chunk must have started from its predecessor's exit state; the rare
-//                   chunk that did not is run again, in order, with its entry forced -- correctness does not
+//                   chunk that did not is repaired, in order: one thread walks its sub-sequences again from the
+//                   true entry state until a walk falls into step with the old records -- correctness does not
 //                   depend on luck;
 //   k_sync_cta_scan exclusive prefix of block counts and DC sums over the chunks -> first block index and DC
 //                   predictors of every chunk;
@@ -972,8 +973,8 @@ k_sync_chunks(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs
 }
 
 // One CTA per image: every chunk must have started from the state its predecessor ended in. All threads compare; the
-// first chunk that does not is run again with its entry forced, then the search goes on behind it (its exit state may have
-// changed). With pre-lanes this finds nothing in almost every image and costs one pass over the chunk states.
+// first chunk that does not is repaired by one thread (sync_repair_chunk), then the search goes on behind it (its exit state
+// may have changed). With pre-lanes this finds nothing in almost every image and costs one pass over the chunk states.
 __global__ void __launch_bounds__(kHuffThreads)
 k_sync_sweep(const uint8_t *__restrict__ clean, const ImgDev *__restrict__ imgs, const uint32_t *__restrict__ sync_imgs,
              const uint32_t *__restrict__ clean_len, const uint16_t *__restrict__ luts, SubRec *__restrict__ recs,
