@@ -33,6 +33,8 @@
  *                                               in and out; _ex: output layout, host threads for parsing/staging
  *   b2j_decode_host_multi   main.cpp:17-37      one call over several GPUs: images are sharded by compressed bytes,
  *                                               one host thread and one context per GPU, no exchange between them
+ *   b2j_idct_*              idct.h:9-18         the device backend as the reference's own decoder.cpp drives it
+ *                                               (coefficients in, pixels out): see "secondary boundary" below
  *   b2j_read_files          decoder.cpp:94-101  the 2 KiB fread() loop (and main.cpp's fopen): whole files read with
  *                                               several threads into one pinned arena
  *   b2j_host_alloc/free     oclDCT8x8.cpp:112-165 the host side of clidct_allocate_memory(): pinned buffers, so that
@@ -51,7 +53,7 @@
 extern "C" {
 #endif
 
-#define B2J_ABI_VERSION 3
+#define B2J_ABI_VERSION 4
 
 /* ---- return codes (0 = success, like the reference's `true`) ---- */
 #define B2J_OK 0
@@ -252,6 +254,29 @@ void b2j_host_free(void *p);
  * what to pass to b2j_host_free() afterwards. A file that cannot be read gets files[i] = NULL, lens[i] = 0 and the
  * call returns B2J_E_ARG after reading the others. */
 int b2j_read_files(int n, const char *const *paths, int n_threads, void **arena, const uint8_t **files, size_t *lens);
+
+/* ------------------------------------------------------------------ secondary boundary -- */
+/* Coefficients in, pixels out: the reference's device backend (idct.h:9-18, oclDCT8x8.cpp) as it is driven by the
+ * reference's own decoder.cpp, which entropy-decodes on the CPU and hands over int32 coefficients that are already
+ * dequantised. csrc/refshim/idct_b2j.cpp implements the ten clidct_* functions on these calls.
+ *   b2j_idct_create        clidct_create() + clidct_allocate_memory() + clidct_build()   (idct.h:10-11,13)
+ *   b2j_idct_upload        clidct_transfer_data_to_device()                              (idct.h:12)
+ *   b2j_idct_run           clidct_run() + clidct_wait_for_completion()                   (idct.h:14,17)
+ *   b2j_idct_read_pixels   clidct_retrieve_image_from_device()                           (idct.h:16)
+ *   b2j_idct_read_coefs    clidct_retrieve_data_from_device()                            (idct.h:15)
+ *   b2j_idct_destroy       clidct_clean_up()                                             (idct.h:18)
+ * Luma sampling luma_h x luma_v with 1x1 chroma: the reference's YUV444 is (1,1), its YUV411 (2,2). The coefficients are
+ * int32 [blk_count][64], natural order, MCU-interleaved block order (JPG_DATA::mcu_data, jpeg.h:74); they are held as
+ * int16 on the device (saturated; an 8-bit baseline JPEG keeps them inside +-2^15). The pixels equal the reference's CPU
+ * path (cpuIDCT8x8 + YUV_to_RGB32), not the OpenCL kernel's float colour. */
+typedef struct b2j_idct b2j_idct;
+int b2j_idct_create(b2j_ctx *ctx, int width, int height, int luma_h, int luma_v, b2j_idct **out);
+int b2j_idct_blk_count(const b2j_idct *p);
+int b2j_idct_upload(b2j_idct *p, const int32_t *coefs, int offset, int count);
+int b2j_idct_run(b2j_idct *p);
+int b2j_idct_read_pixels(b2j_idct *p, uint8_t *bgra /* width*height*4 */);
+int b2j_idct_read_coefs(b2j_idct *p, int32_t *coefs /* blk_count*64 */);
+void b2j_idct_destroy(b2j_idct *p);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,8 @@ EXPORTED_SYMBOLS = [
     "b2j_batch_upload", "b2j_batch_set_output_format", "b2j_batch_decode", "b2j_batch_decode_timed", "b2j_batch_decode_steps", "b2j_batch_sync", "b2j_batch_status", "b2j_batch_sync_stats",
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
     "b2j_batch_read_coefs", "b2j_decode_host", "b2j_decode_host_ex", "b2j_decode_host_multi", "b2j_host_alloc", "b2j_host_free",
-    "b2j_read_files",
+    "b2j_read_files", "b2j_idct_create", "b2j_idct_blk_count", "b2j_idct_upload", "b2j_idct_run", "b2j_idct_read_pixels", "b2j_idct_read_coefs",
+    "b2j_idct_destroy",
 ]
 
 
@@ -126,6 +127,14 @@ def load_library():
     L.b2j_host_free.argtypes = [vp]
     L.b2j_host_free.restype = None
     L.b2j_read_files.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.b2j_idct_create.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
+    L.b2j_idct_blk_count.argtypes = [vp]
+    L.b2j_idct_upload.argtypes = [vp, vp, ci, ci]
+    L.b2j_idct_run.argtypes = [vp]
+    L.b2j_idct_read_pixels.argtypes = [vp, vp]
+    L.b2j_idct_read_coefs.argtypes = [vp, vp]
+    L.b2j_idct_destroy.argtypes = [vp]
+    L.b2j_idct_destroy.restype = None
     _LIB = L
     return L
 
@@ -293,6 +302,45 @@ class Decoder:
         status = np.zeros(n, np.int32)
         _check(self.lib.b2j_decode_host_ex(self._h, n, fp, ln, ctypes.byref(opts), op, status.ctypes.data), "b2j_decode_host_ex")
         return outs, status
+
+
+class Idct:
+    """b2j_idct: the secondary boundary -- dequantised int32 coefficients in, BGRA pixels out (the clidct_* functions)."""
+
+    def __init__(self, dec, width, height, luma_h, luma_v):
+        self.dec, self.lib = dec, dec.lib
+        self.width, self.height = width, height
+        self._h = ctypes.c_void_p()
+        _check(self.lib.b2j_idct_create(dec._h, width, height, luma_h, luma_v, ctypes.byref(self._h)), "b2j_idct_create")
+        self.blk_count = self.lib.b2j_idct_blk_count(self._h)
+
+    def upload(self, coefs, offset=0):
+        coefs = np.ascontiguousarray(coefs, np.int32)
+        _check(self.lib.b2j_idct_upload(self._h, coefs.ctypes.data, offset, coefs.shape[0]), "b2j_idct_upload")
+
+    def run(self):
+        _check(self.lib.b2j_idct_run(self._h), "b2j_idct_run")
+
+    def pixels(self):
+        out = np.zeros((self.height, self.width, 4), np.uint8)
+        _check(self.lib.b2j_idct_read_pixels(self._h, out.ctypes.data), "b2j_idct_read_pixels")
+        return out
+
+    def coefs(self):
+        out = np.zeros((self.blk_count, 64), np.int32)
+        _check(self.lib.b2j_idct_read_coefs(self._h, out.ctypes.data), "b2j_idct_read_coefs")
+        return out
+
+    def close(self):
+        if self._h:
+            self.lib.b2j_idct_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:

@@ -1681,6 +1681,21 @@ k_expand_coefs(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt
     out[i] = (int32_t)coef[i] * (int32_t)qtab[comp * 64 + k];
 }
 
+// The secondary boundary (idct.h:9-18): the reference hands its device backend int32 coefficients that are already
+// dequantised. They go into the int16 plane as they are (saturated: a valid 8-bit JPEG keeps them inside +-2^15) and
+// the IDCT/colour kernel runs with unit quantisers.
+__global__ void __launch_bounds__(256)
+k_pack_coefs(const int32_t *__restrict__ in, int16_t *__restrict__ coef, size_t n_values)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n_values) return;   // n_values is a multiple of 64
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(in + i));
+    uint32_t lo, hi;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(lo) : "r"(v.y), "r"(v.x));
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(hi) : "r"(v.w), "r"(v.z));
+    *reinterpret_cast<uint2 *>(coef + i) = make_uint2(lo, hi);
+}
+
 // =====================================================================================
 // Launchers (host).
 size_t huff_smem_bytes(uint32_t max_lut_len) { return (size_t)kHuffThreads * 128 + kZzBytes + (size_t)max_lut_len * 2; }
@@ -1766,6 +1781,13 @@ void launch_idct(const DecodeArgs &a, const PartRange &r, cudaStream_t s)
     if (count[kTileGeneric]) { B2J_IDCT_BY_FORMAT(kTileGeneric) }
 #undef B2J_IDCT_BY_FORMAT
 #undef B2J_IDCT_LAUNCH
+}
+
+void launch_pack(const int32_t *in, int16_t *coef, size_t n_values, cudaStream_t s)
+{
+    if (n_values == 0) return;
+    const size_t threads = (n_values + 3) / 4;
+    k_pack_coefs<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(in, coef, n_values);
 }
 
 void launch_expand(const int16_t *coef, const uint16_t *qtab, uint32_t blk_count, uint32_t tot, uint32_t ny, uint32_t nu, int32_t *out, cudaStream_t s)

@@ -327,10 +327,22 @@ extern "C" void b2j_destroy(b2j_ctx *ctx)
     delete ctx;
 }
 
+// coef_only: a batch for the secondary boundary (b2j_idct_*): no scan, no decode tables, unit quantisers -- the
+// coefficient plane is filled from outside, only launch_idct() runs on it.
+static int batch_create_impl(b2j_ctx *ctx, int n, const b2j_image_desc *descs, const uint8_t *const *files,
+                             const size_t *lens, bool coef_only, b2j_batch **out);
+
 extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs, const uint8_t *const *files,
                                 const size_t *lens, b2j_batch **out)
 {
-    if (!ctx || n <= 0 || !descs || !files || !lens || !out) return B2J_E_ARG;
+    if (!files || !lens) return B2J_E_ARG;
+    return batch_create_impl(ctx, n, descs, files, lens, false, out);
+}
+
+static int batch_create_impl(b2j_ctx *ctx, int n, const b2j_image_desc *descs, const uint8_t *const *files,
+                             const size_t *lens, bool coef_only, b2j_batch **out)
+{
+    if (!ctx || n <= 0 || !descs || !out) return B2J_E_ARG;
     *out = nullptr;
     CU_TRY(cudaSetDevice(ctx->device));
 
@@ -370,12 +382,13 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         memset(&im, 0, sizeof(im));
         // bit positions are 32-bit on the device (scan_size * 8 must fit); an empty scan (file cut right behind the SOS
         // header) has nothing to decode -- the reference fails it with "data incomplete" (decoder.cpp:310-314)
-        if (d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset || d.scan_size == 0 || d.scan_size >= 0x1FFFFFFFull || !geometry_ok(d))
+        if (coef_only) { if (!geometry_ok(d)) { rc = B2J_E_ARG; break; } }
+        else if (d.scan_offset > lens[i] || d.scan_size > lens[i] - d.scan_offset || d.scan_size == 0 || d.scan_size >= 0x1FFFFFFFull || !geometry_ok(d))
         { rc = d.scan_size == 0 && d.scan_offset <= lens[i] ? B2J_E_DATA : B2J_E_ARG; break; }
         img_cta0[(size_t)i] = (uint32_t)ctas.size(); img_tile0[(size_t)i] = (uint32_t)tiles.size(); img_chunk0[(size_t)i] = (uint32_t)chunk_img.size();
         img_scta0[(size_t)i] = (uint32_t)sctas.size(); img_simg0[(size_t)i] = (uint32_t)simgs.size();
         im.raw_off = raw_total;
-        im.raw_len = (uint32_t)d.scan_size;
+        im.raw_len = coef_only ? 0u : (uint32_t)d.scan_size;
         raw_total += align_up((size_t)im.raw_len + 32, 16);
         im.pix_off = pix_total;
         pix_total += align_up((size_t)d.width * d.height * 4, 256);
@@ -389,7 +402,8 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         im.seg_first = seg_total;
         im.n_segs = (im.mcu_count + im.restart_interval - 1) / im.restart_interval;
         seg_total += im.n_segs;
-        if (im.has_dri)
+        if (coef_only) { /* no entropy stage: no decode CTAs of either kind */ }
+        else if (im.has_dri)
             for (uint32_t s = 0; s < im.n_segs; s += kHuffThreads) ctas.push_back({(uint32_t)i, s});
         else
         {
@@ -424,10 +438,13 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         for (int c = 0; c < 3; c++)
             for (int k = 0; k < 64; k++)
             {
-                const uint16_t q = d.quant[d.quant_id[c]][k];
+                const uint16_t q = coef_only ? (uint16_t)1 : d.quant[d.quant_id[c]][k];
                 qtabs[(size_t)i * 192 + (size_t)c * 64 + zz[k]] = q;
                 if (q > 255) im.wide_q = 1;
             }
+        pixels += (int64_t)d.width * d.height;
+        if (coef_only) continue;
+        scan_bytes += (int64_t)d.scan_size;
         // decode tables, shared between images that carry identical DHT payloads
         std::string key;
         for (int c = 0; c < 3; c++)
@@ -459,8 +476,6 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
         if (im.lut_len > max_lut_len) max_lut_len = im.lut_len;
         if (im.lut_dec_len > max_lut_dec_len) max_lut_dec_len = im.lut_dec_len;
         if (im.lut_len - im.lut_dec_len > max_lut_walk_len) max_lut_walk_len = im.lut_len - im.lut_dec_len;
-        pixels += (int64_t)d.width * d.height;
-        scan_bytes += (int64_t)d.scan_size;
     }
     if (rc != B2J_OK) { delete b; return rc; }
     if (blk_total + kTileBlocks >= 0xFFFFFFF0ull) { delete b; return B2J_E_ARG; }
@@ -560,7 +575,7 @@ extern "C" int b2j_batch_create(b2j_ctx *ctx, int n, const b2j_image_desc *descs
     {
         const ImgDev &im = b->imgs[(size_t)i];
         uint8_t *dst = b->h_blob + b->off_raw + im.raw_off;
-        memcpy(dst, files[i] + descs[i].scan_offset, im.raw_len);
+        if (im.raw_len) memcpy(dst, files[i] + descs[i].scan_offset, im.raw_len);
         // pad with FF D9 D9 ...: running off the end of a scan then looks like EOI to the pre-pass
         memset(dst + im.raw_len, 0xD9, align_up((size_t)im.raw_len + 32, 16) - im.raw_len);
         dst[im.raw_len] = 0xFF;
@@ -1208,4 +1223,106 @@ extern "C" int b2j_decode_host(b2j_ctx *ctx, int n, const uint8_t *const *files,
     if (const char *ge = getenv("B2J_HOST_GROUP")) o.group = atoi(ge);
     if (const char *te = getenv("B2J_HOST_THREADS")) o.n_threads = atoi(te);
     return b2j_decode_host_ex(ctx, n, files, lens, &o, out_bgra, status);
+}
+
+// ---------------------------------------------------------------------------------------
+// The secondary boundary (reference idct.h:9-18, oclDCT8x8.cpp): coefficients in, pixels out.
+
+struct b2j_idct
+{
+    b2j_batch *b;          // a coefficient-only batch of one image: tiles, unit quantisers, plane, pixels
+    int32_t *d_in;         // the uploaded int32 coefficients (kept: clidct_retrieve_data_from_device reads them back)
+    size_t d_in_cap;
+    int blk_count;
+};
+
+extern "C" int b2j_idct_create(b2j_ctx *ctx, int width, int height, int luma_h, int luma_v, b2j_idct **out)
+{
+    if (!ctx || !out || width <= 0 || height <= 0 || luma_h < 1 || luma_h > 4 || luma_v < 1 || luma_v > 4) return B2J_E_ARG;
+    *out = nullptr;
+    b2j_image_desc d;
+    memset(&d, 0, sizeof(d));
+    d.width = width; d.height = height;
+    d.sampling[0] = (uint8_t)((luma_h << 4) | luma_v); d.sampling[1] = d.sampling[2] = 0x11;
+    d.color_space = (luma_h == 1 && luma_v == 1) ? B2J_CS_YUV444 : ((luma_h == 2 && luma_v == 2) ? B2J_CS_YUV411 : B2J_CS_OTHER);
+    d.mcu_width = 8 * luma_h; d.mcu_height = 8 * luma_v;
+    d.mcu_count_w = (width - 1) / d.mcu_width + 1; d.mcu_count_h = (height - 1) / d.mcu_height + 1;
+    d.mcu_count = d.mcu_count_w * d.mcu_count_h;
+    d.blks_per_mcu[0] = luma_h * luma_v; d.blks_per_mcu[1] = d.blks_per_mcu[2] = 1;
+    d.tot_blks_per_mcu = luma_h * luma_v + 2;
+    d.blk_count = d.mcu_count * d.tot_blks_per_mcu;
+    b2j_idct *p = new b2j_idct;
+    p->b = nullptr; p->d_in = nullptr; p->d_in_cap = 0; p->blk_count = d.blk_count;
+    int rc = batch_create_impl(ctx, 1, &d, nullptr, nullptr, true, &p->b);
+    if (rc == B2J_OK)
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaError_t e = ctx->dev_pool.get((size_t)d.blk_count * 256, (void **)&p->d_in, &p->d_in_cap);
+        if (e != cudaSuccess) { cudaGetLastError(); rc = B2J_E_NOMEM; }
+    }
+    if (rc == B2J_OK) rc = b2j_batch_upload(p->b, nullptr);   // descriptors, tiles, quantisers
+    if (rc != B2J_OK) { b2j_idct_destroy(p); return rc; }
+    *out = p;
+    return B2J_OK;
+}
+
+extern "C" int b2j_idct_blk_count(const b2j_idct *p) { return p ? p->blk_count : B2J_E_ARG; }
+
+extern "C" int b2j_idct_upload(b2j_idct *p, const int32_t *coefs, int offset, int count)
+{
+    if (!p || !coefs || offset < 0 || count < 0 || offset > p->blk_count || count > p->blk_count - offset) return B2J_E_ARG;
+    b2j_batch *b = p->b;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, nullptr);
+    CU_TRY(cudaMemcpyAsync(p->d_in + (size_t)offset * 64, coefs, (size_t)count * 256, cudaMemcpyHostToDevice, s));
+    launch_pack(p->d_in + (size_t)offset * 64, b->d_coef + (size_t)offset * 64, (size_t)count * 64, s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));   // the caller's buffer may be pageable and reused
+    return B2J_OK;
+}
+
+extern "C" int b2j_idct_run(b2j_idct *p)
+{
+    if (!p) return B2J_E_ARG;
+    b2j_batch *b = p->b;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, nullptr);
+    CU_TRY(cudaMemsetAsync(b->args.status, 0, 4, s));
+    launch_idct(b->args, b->parts[0], s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" int b2j_idct_read_pixels(b2j_idct *p, uint8_t *dst)
+{
+    if (!p) return B2J_E_ARG;
+    return b2j_batch_read_pixels(p->b, nullptr, 0, dst);
+}
+
+extern "C" int b2j_idct_read_coefs(b2j_idct *p, int32_t *dst)
+{
+    if (!p || !dst) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(p->b->ctx->device));
+    cudaStream_t s = pick_stream(p->b, nullptr);
+    CU_TRY(cudaMemcpyAsync(dst, p->d_in, (size_t)p->blk_count * 256, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+extern "C" void b2j_idct_destroy(b2j_idct *p)
+{
+    if (!p) return;
+    if (p->b)
+    {
+        b2j_ctx *ctx = p->b->ctx;
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->dev_pool.put(p->d_in, p->d_in_cap);
+        }
+        b2j_batch_destroy(p->b);
+    }
+    delete p;
 }

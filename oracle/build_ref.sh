@@ -32,4 +32,13 @@ if [ -f "$root/ocljpegdecoder_b200/lib/libb2j.so" ]; then
         -L"$root/ocljpegdecoder_b200/lib" -lb2j -Wl,-rpath,'$ORIGIN/../../ocljpegdecoder_b200/lib' \
         -o "$here/_ref/ocljpegdec_b2j"
     echo "built $here/_ref/ocljpegdec_b2j (reference main+parser on the B200 decoder shim)"
+    # The secondary boundary: the reference's own decoder.cpp too, unmodified and WITHOUT USE_CPU_ONLY (its
+    # device branch: CPU Huffman, then the ten clidct_* calls of idct.h:9-18), linked against this repo's
+    # clidct shim instead of oclDCT8x8.cpp.
+    g++ -std=c++11 -O2 -DNDEBUG -w -DB2J_USE_REFERENCE_HEADERS -I"$src" \
+        "$src/main.cpp" "$src/parser.cpp" "$src/bitstream.cpp" "$src/huffman.cpp" "$src/decoder.cpp" "$src/cpuIDCT8x8.cpp" \
+        "$root/ocljpegdecoder_b200/csrc/refshim/idct_b2j.cpp" \
+        -L"$root/ocljpegdecoder_b200/lib" -lb2j -Wl,-rpath,'$ORIGIN/../../ocljpegdecoder_b200/lib' \
+        -o "$here/_ref/ocljpegdec_b2jidct"
+    echo "built $here/_ref/ocljpegdec_b2jidct (reference main+parser+decoder on the B200 clidct shim)"
 fi

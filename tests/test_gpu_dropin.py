@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 
 CLI = os.path.join(ROOT, "ocljpegdecoder_b200", "bin", "b2jdec")
 REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "ocljpegdec_b2j")
+REF_IDCT = os.path.join(ROOT, "oracle", "_ref", "ocljpegdec_b2jidct")
 
 
 def _run(binary, jpeg_path, env_extra=None):
@@ -67,4 +68,18 @@ def test_reference_main_and_parser_on_the_shim(built, oracle):
         log, bmp = _run(REF_MAIN, path)
         assert "decoding completed" in log and "End of Image" in log, log
         rc, img, _, bgra = oracle.decode(open(path, "rb").read(), gate=gate)
+        _check_bmp(bmp, img.width, img.height, bgra)
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_IDCT), reason="oracle/_ref/ocljpegdec_b2jidct not built (needs /root/reference)")
+def test_reference_decoder_on_the_clidct_shim(built, oracle):
+    """The secondary boundary (idct.h:9-18): the reference's own main.cpp + parser.cpp + decoder.cpp, unmodified and built
+    without USE_CPU_ONLY -- CPU Huffman, then clidct_create / allocate_memory / build / transfer / run / wait / retrieve /
+    clean_up -- linked against csrc/refshim/idct_b2j.cpp in place of oclDCT8x8.cpp. The BMP must hold the pixels of the
+    reference's CPU path."""
+    for name in ("JPEG_example_JPG_RIP_050", "g444_ri5_opt_q95"):
+        path = os.path.join(GOLDEN, name + ".jpg")
+        log, bmp = _run(REF_IDCT, path)
+        assert "clidct_run()" in log and "decoding completed" in log, log
+        rc, img, _, bgra = oracle.decode(open(path, "rb").read(), gate=0)
         _check_bmp(bmp, img.width, img.height, bgra)

@@ -720,3 +720,27 @@ def test_decode_host_multi_and_pinned_buffers(decoder, oracle, tmp_path):
             d.close()
         pinned.close()
         b2j.host_free(arena)
+
+
+def test_secondary_boundary_coefficients_in_pixels_out(decoder, oracle):
+    """b2j_idct_*: the reference's coefficient tap (int32, dequantised: what its decoder.cpp hands to clidct_transfer_data_to_device)
+    in, the pixels of its CPU path out -- 4:4:4 and 4:2:0 as the reference knows them, 4:2:2 / 4:4:0 beyond; odd sizes; upload in
+    two pieces; the coefficients read back as they were sent."""
+    import ocljpegdecoder_b200 as b2j
+    for w, h, ss, hv, q in [(200, 120, "444", (1, 1), 85), (131, 77, "420", (2, 2), 75), (640, 480, "420", (2, 2), 95), (322, 98, "422", (2, 1), 60)]:
+        data = synth.synth_jpeg(w, h, 40 + w, q, ss, 0)
+        oracle.set_strict(False)
+        try:
+            rc, img, coef, bgra = oracle.decode(data, 1)
+        finally:
+            oracle.set_strict(True)
+        assert rc == 0
+        idct = b2j.Idct(decoder, w, h, hv[0], hv[1])
+        assert idct.blk_count == coef.shape[0]
+        half = coef.shape[0] // 2
+        idct.upload(coef[half:], offset=half)
+        idct.upload(coef[:half], offset=0)
+        idct.run()
+        assert np.array_equal(idct.pixels(), bgra), (w, h, ss)
+        assert np.array_equal(idct.coefs(), coef)
+        idct.close()
