@@ -11,7 +11,10 @@
 namespace b2j {
 
 // ---------------------------------------------------------------- constants ------------
-constexpr int kScanGroups = 4;           // 16-byte groups per thread in the pre-pass (4 loads in flight per thread)
+#ifndef B2J_SCAN_GROUPS
+#define B2J_SCAN_GROUPS 4
+#endif
+constexpr int kScanGroups = B2J_SCAN_GROUPS;           // 16-byte groups per thread in the pre-pass (4 loads in flight per thread)
 constexpr int kScanThreads = 256;
 constexpr int kScanChunkBytes = kScanThreads * kScanGroups * 16;   // bytes of raw scan one CTA of the pre-pass handles
 constexpr int kHuffThreads = 128;        // decode lanes (= segments) per Huffman CTA
