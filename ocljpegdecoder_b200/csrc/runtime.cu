@@ -1033,9 +1033,18 @@ extern "C" int b2j_decode_host_ex(b2j_ctx *ctx, int n, const uint8_t *const *fil
         if (G.done) cudaEventDestroy(G.done);
         G.decoded = G.done = nullptr;
     };
+    const int max_in_flight = window + 4;   // groups enqueued and not yet back: bounds the buffers the pools ever hold, so that
+                                            // after the first call no group waits for a cudaMalloc / cudaHostAlloc
     for (int g = 0; g < ng && rc == B2J_OK; g++)
     {
         FeedGroup &G = groups[(size_t)g];
+        while (g - oldest >= max_in_flight)
+        {
+            FeedGroup &O = groups[(size_t)oldest];
+            if (!O.closed && O.done) cudaEventSynchronize(O.done);
+            close_group(O);
+            oldest++;
+        }
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return G.ready; });
