@@ -33,6 +33,7 @@
  *                                               in and out; _ex: output layout, host threads for parsing/staging
  *   b2j_decode_host_multi   main.cpp:17-37      one call over several GPUs: images are sharded by compressed bytes,
  *                                               one host thread and one context per GPU, no exchange between them
+ *   b2j_batch_downscale     (none)              reduced copies of the decoded pixels for consumers
  *   b2j_idct_*              idct.h:9-18         the device backend as the reference's own decoder.cpp drives it
  *                                               (coefficients in, pixels out): see "secondary boundary" below
  *   b2j_read_files          decoder.cpp:94-101  the 2 KiB fread() loop (and main.cpp's fopen): whole files read with
@@ -53,7 +54,7 @@
 extern "C" {
 #endif
 
-#define B2J_ABI_VERSION 4
+#define B2J_ABI_VERSION 5
 
 /* ---- return codes (0 = success, like the reference's `true`) ---- */
 #define B2J_OK 0
@@ -216,6 +217,14 @@ int b2j_batch_read_all_pixels(b2j_batch *batch, void *stream, uint8_t *const *ds
 /* The reference's coefficient tap: int32[blk_count][64], natural order, dequantised on the
  * device by a small expansion kernel, then copied (synchronises). */
 int b2j_batch_read_coefs(b2j_batch *batch, void *stream, int image, int32_t *dst);
+
+/* Output stage for consumers that want smaller images: box-filter reduction of the decoded pixels by
+ * factor 2, 4 or 8 per axis, after b2j_batch_decode(), in the batch's output format. Reduced size: ceil(w/f) x ceil(h/f);
+ * every value is the rounded mean (sum + n/2) / n of the n input values it covers (at the right / bottom edge: of those that
+ * exist). The full-size pixels stay where they are. */
+int b2j_batch_downscale(b2j_batch *batch, void *stream, int factor);
+int b2j_batch_downscaled_device(const b2j_batch *batch, int image, void **dptr, size_t *nbytes, int *width, int *height);
+int b2j_batch_read_downscaled(b2j_batch *batch, void *stream, int image, uint8_t *dst);   /* synchronises */
 
 /* Whole path with host buffers in and out: parse, upload, decode, download.
  * out_bgra[i] must hold width*height*4 bytes (use b2j_parse_header() to size it); images whose

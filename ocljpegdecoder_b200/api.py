@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "b2j_batch_pixels_device", "b2j_batch_coefs_device", "b2j_batch_read_pixels", "b2j_batch_read_all_pixels",
     "b2j_batch_read_coefs", "b2j_decode_host", "b2j_decode_host_ex", "b2j_decode_host_multi", "b2j_host_alloc", "b2j_host_free",
     "b2j_read_files", "b2j_idct_create", "b2j_idct_blk_count", "b2j_idct_upload", "b2j_idct_run", "b2j_idct_read_pixels", "b2j_idct_read_coefs",
-    "b2j_idct_destroy",
+    "b2j_idct_destroy", "b2j_batch_downscale", "b2j_batch_downscaled_device", "b2j_batch_read_downscaled",
 ]
 
 
@@ -127,6 +127,9 @@ def load_library():
     L.b2j_host_free.argtypes = [vp]
     L.b2j_host_free.restype = None
     L.b2j_read_files.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.b2j_batch_downscale.argtypes = [vp, vp, ci]
+    L.b2j_batch_downscaled_device.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.b2j_batch_read_downscaled.argtypes = [vp, vp, ci, vp]
     L.b2j_idct_create.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
     L.b2j_idct_blk_count.argtypes = [vp]
     L.b2j_idct_upload.argtypes = [vp, vp, ci, ci]
@@ -426,6 +429,20 @@ class Batch:
         d = self.descs[i]
         out = np.zeros((d.blk_count, 64), np.int32)
         _check(self.lib.b2j_batch_read_coefs(self._h, stream, i, out.ctypes.data), "b2j_batch_read_coefs")
+        return out
+
+    def downscale(self, factor, stream=None):
+        """b2j_batch_downscale: box-filter reduction (factor 2, 4 or 8) of the decoded pixels, in the batch's output format."""
+        _check(self.lib.b2j_batch_downscale(self._h, stream, factor), "b2j_batch_downscale")
+        self.small_factor = factor
+
+    def downscaled(self, i, stream=None):
+        d, f = self.descs[i], self.small_factor
+        ow, oh = (d.width + f - 1) // f, (d.height + f - 1) // f
+        fmt = getattr(self, "out_format", OUT_BGRA)
+        shape = (oh, ow, 4) if fmt == OUT_BGRA else ((oh, ow, 3) if fmt == OUT_RGB24 else (3, oh, ow))
+        out = np.zeros(shape, np.uint8)
+        _check(self.lib.b2j_batch_read_downscaled(self._h, stream, i, out.ctypes.data), "b2j_batch_read_downscaled")
         return out
 
     def pixels_device(self, i):

@@ -123,6 +123,9 @@ struct b2j_batch
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
     int32_t *d_expand; size_t d_expand_cap;   // lazily allocated for the coefficient tap
+    uint8_t *d_small; size_t d_small_cap;     // lazily allocated: the reduced pixels of b2j_batch_downscale() behind a table of offsets
+    int small_factor;                         // 0 = none yet
+    std::vector<uint64_t> small_off;          // byte offset of every image's reduced pixels behind the offset table
 
     CUtensorMap tmap;
     DecodeArgs args;
@@ -217,8 +220,9 @@ void release_batch_buffers(b2j_batch *b)
     c->dev_pool.put(b->d_coef, b->d_coef_cap);
     c->dev_pool.put(b->d_pix, b->d_pix_cap);
     c->dev_pool.put(b->d_expand, b->d_expand_cap);
+    c->dev_pool.put(b->d_small, b->d_small_cap);
     b->h_blob = b->d_blob = b->d_scratch = b->d_pix = nullptr;
-    b->d_coef = nullptr; b->d_expand = nullptr;
+    b->d_coef = nullptr; b->d_expand = nullptr; b->d_small = nullptr;
 }
 
 } // namespace
@@ -352,7 +356,7 @@ static int batch_create_impl(b2j_ctx *ctx, int n, const b2j_image_desc *descs, c
     b->descs.assign(descs, descs + n);
     b->imgs.resize((size_t)n);
     b->h_blob = b->d_blob = b->d_scratch = b->d_pix = nullptr;
-    b->d_coef = nullptr; b->d_expand = nullptr;
+    b->d_coef = nullptr; b->d_expand = nullptr; b->d_small = nullptr; b->d_small_cap = 0; b->small_factor = 0;
     b->h_blob_cap = b->d_blob_cap = b->d_scratch_cap = b->d_coef_cap = b->d_pix_cap = b->d_expand_cap = 0;
     b->uploaded = false;
     b->last_stream = nullptr;
@@ -880,6 +884,84 @@ extern "C" int b2j_batch_read_coefs(b2j_batch *b, void *stream, int image, int32
                   b->d_expand, s);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(dst, b->d_expand, bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return B2J_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Output stage: reduced copies of the decoded pixels.
+static void small_dims(const ImgDev &im, int f, uint32_t *ow, uint32_t *oh)
+{
+    *ow = (im.width + (uint32_t)f - 1) / (uint32_t)f;
+    *oh = (im.height + (uint32_t)f - 1) / (uint32_t)f;
+}
+
+extern "C" int b2j_batch_downscale(b2j_batch *b, void *stream, int factor)
+{
+    if (!b || (factor != 2 && factor != 4 && factor != 8)) return B2J_E_ARG;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    const int fmt = b->args.out_format;
+    const size_t bpp = fmt == B2J_OUT_BGRA ? 4 : 3;
+    const size_t table = align_up(8 * (size_t)b->n, 256);
+    if (b->small_factor != factor || b->small_off.size() != (size_t)b->n)
+    {
+        b->small_off.resize((size_t)b->n);
+        size_t off = table;
+        for (int i = 0; i < b->n; i++)
+        {
+            uint32_t ow, oh;
+            small_dims(b->imgs[(size_t)i], factor, &ow, &oh);
+            b->small_off[(size_t)i] = off;
+            off += align_up((size_t)ow * oh * 4, 16);   // sized for BGRA: every format fits
+        }
+        if (b->d_small_cap < off)
+        {
+            std::lock_guard<std::mutex> lk(b->ctx->mu);
+            b->ctx->dev_pool.put(b->d_small, b->d_small_cap);
+            b->d_small = nullptr; b->d_small_cap = 0;
+            cudaError_t e = b->ctx->dev_pool.get(off, (void **)&b->d_small, &b->d_small_cap);
+            if (e != cudaSuccess) { cudaGetLastError(); return B2J_E_NOMEM; }
+        }
+        b->small_factor = factor;
+        CU_TRY(cudaMemcpyAsync(b->d_small, b->small_off.data(), 8 * (size_t)b->n, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));   // the table is a pageable vector that may be rebuilt
+    }
+    uint32_t max_samples = 0;
+    for (int i = 0; i < b->n; i++)
+    {
+        uint32_t ow, oh;
+        small_dims(b->imgs[(size_t)i], factor, &ow, &oh);
+        const uint32_t ns = ow * oh * (fmt == B2J_OUT_RGB_PLANAR ? 3u : 1u);
+        if (ns > max_samples) max_samples = ns;
+    }
+    (void)bpp;
+    launch_downscale(b->d_pix, b->args.imgs, reinterpret_cast<const uint64_t *>(b->d_small), b->d_small, (uint32_t)b->n, max_samples, (uint32_t)factor, fmt, s);
+    CU_TRY(cudaGetLastError());
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_downscaled_device(const b2j_batch *b, int image, void **dptr, size_t *nbytes, int *width, int *height)
+{
+    if (!b || image < 0 || image >= b->n || !dptr || !b->small_factor) return B2J_E_ARG;
+    uint32_t ow, oh;
+    small_dims(b->imgs[(size_t)image], b->small_factor, &ow, &oh);
+    *dptr = b->d_small + b->small_off[(size_t)image];
+    if (nbytes) *nbytes = (size_t)ow * oh * (b->args.out_format == B2J_OUT_BGRA ? 4u : 3u);
+    if (width) *width = (int)ow;
+    if (height) *height = (int)oh;
+    return B2J_OK;
+}
+
+extern "C" int b2j_batch_read_downscaled(b2j_batch *b, void *stream, int image, uint8_t *dst)
+{
+    void *p = nullptr; size_t nb = 0;
+    if (!dst) return B2J_E_ARG;
+    const int rc = b2j_batch_downscaled_device(b, image, &p, &nb, nullptr, nullptr);
+    if (rc != B2J_OK) return rc;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = pick_stream(b, stream);
+    CU_TRY(cudaMemcpyAsync(dst, p, nb, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     return B2J_OK;
 }

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(L, name), "missing export " + name
     assert sorted(declared) == sorted(b2j.EXPORTED_SYMBOLS)
-    assert L.b2j_abi_version() == 4
+    assert L.b2j_abi_version() == 5
 
 
 def test_struct_sizes_match_header(built):

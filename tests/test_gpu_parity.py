@@ -744,3 +744,39 @@ def test_secondary_boundary_coefficients_in_pixels_out(decoder, oracle):
         assert np.array_equal(idct.pixels(), bgra), (w, h, ss)
         assert np.array_equal(idct.coefs(), coef)
         idct.close()
+
+
+def test_downscaled_output(decoder):
+    """b2j_batch_downscale: box-filter reduction by 2, 4, 8 in every output format against numpy: sizes that are and are not
+    multiples of the factor (edge means over the pixels that exist), rounding (sum + n/2) // n."""
+    import ocljpegdecoder_b200 as b2j
+    files = [synth.synth_jpeg(w, h, 60 + w, q, ss, ri) for w, h, ss, q, ri in [(320, 240, "420", 90, 8), (131, 77, "444", 85, 0), (65, 33, "422", 75, 0), (8, 8, "444", 50, 0)]]
+    batch = decoder.batch(files)
+    batch.upload()
+
+    def box(a, f):   # a: [H, W, C] uint8
+        h, w, c = a.shape
+        oh, ow = (h + f - 1) // f, (w + f - 1) // f
+        pad = np.zeros((oh * f, ow * f, c), np.uint32)
+        cnt = np.zeros((oh * f, ow * f, 1), np.uint32)
+        pad[:h, :w] = a
+        cnt[:h, :w] = 1
+        s = pad.reshape(oh, f, ow, f, c).sum(axis=(1, 3))
+        n = cnt.reshape(oh, f, ow, f, 1).sum(axis=(1, 3))
+        return ((s + n // 2) // n).astype(np.uint8)
+
+    for fmt in (b2j.OUT_BGRA, b2j.OUT_RGB24, b2j.OUT_RGB_PLANAR):
+        batch.set_output_format(fmt)
+        batch.decode()
+        assert not batch.status().any()
+        for f in (2, 4, 8):
+            batch.downscale(f)
+            for i in range(len(files)):
+                full = batch.pixels(i)
+                got = batch.downscaled(i)
+                if fmt == b2j.OUT_RGB_PLANAR:
+                    want = np.moveaxis(box(np.moveaxis(full, 0, 2), f), 2, 0)
+                else:
+                    want = box(full, f)
+                assert got.shape == want.shape and np.array_equal(got, want), (fmt, f, i)
+    batch.close()
