@@ -26,6 +26,7 @@ struct DecodeArgs
     // scratch
     uint8_t *clean;
     uint64_t *chunk_state;   // pre-pass: look-back words, zeroed before every decode
+    uint32_t *scan_ticket;   // pre-pass: one chunk-ticket counter per part (launch), zeroed with them
     uint32_t *clean_len, *seg_start;
     SubRec *recs;           // self-synchronising path: one record per sub-sequence
     uint4 *sync_cta_base;   // per chunk (= decode CTA) of the self-synchronising path: (blocks started, DC sums), then their prefix
@@ -51,7 +52,7 @@ struct PartRange { uint32_t img0, img1, chunk0, chunk1, cta0, cta1, tile0, tile1
 cudaError_t init_constants();
 cudaError_t configure_kernels(uint32_t max_lut_len);
 size_t huff_smem_bytes(uint32_t max_lut_len);
-void launch_prepass(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
+void launch_prepass(const DecodeArgs &a, const PartRange &r, uint32_t part, cudaStream_t s);   // 1 kernel
 void launch_huffman(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 1 kernel
 void launch_huffman_sync(const DecodeArgs &a, const PartRange &r, cudaStream_t s);   // 4 kernels
 constexpr int kSyncLaunches = 4;

@@ -118,7 +118,7 @@ struct b2j_batch
 
     // scratch + outputs
     uint8_t *d_scratch; size_t d_scratch_cap;
-    size_t off_clean, off_clean_end, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states, off_zero_end;
+    size_t off_clean, off_clean_end, off_clean_len, off_seg_start, off_status, off_recs, off_pres, off_sync_stats, off_chunk_state, off_chunk_states, off_zero_end, off_ticket;
     size_t scratch_bytes;
     int16_t *d_coef; size_t d_coef_cap; size_t coef_rows;
     uint8_t *d_pix; size_t d_pix_cap; size_t pix_bytes;
@@ -545,6 +545,7 @@ static int batch_create_impl(b2j_ctx *ctx, int n, const b2j_image_desc *descs, c
     b->off_status = place(4 * (size_t)n);
     b->off_sync_stats = place(4 * 8);
     b->off_chunk_state = place(8 * chunk_img.size());
+    b->off_ticket = place(4 * 16);   // one counter per part (at most 16)
     b->off_zero_end = off;
     b->scratch_bytes = off;
     b->n_segs_total = seg_total;
@@ -605,6 +606,7 @@ static int batch_create_impl(b2j_ctx *ctx, int n, const b2j_image_desc *descs, c
     a.tmap = &b->tmap;
     a.clean = b->d_scratch + b->off_clean;
     a.chunk_state = reinterpret_cast<uint64_t *>(b->d_scratch + b->off_chunk_state);
+    a.scan_ticket = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_ticket);
     a.clean_len = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_clean_len);
     a.seg_start = reinterpret_cast<uint32_t *>(b->d_scratch + b->off_seg_start);
     a.status = reinterpret_cast<int32_t *>(b->d_scratch + b->off_status);
@@ -702,7 +704,7 @@ static int enqueue_decode(b2j_batch *b, cudaStream_t s, cudaEvent_t *ev /* event
         const PartRange &r = b->parts[p];
         cudaEvent_t *pe = ev ? ev + 2 + 5 * p : nullptr;
         if (pe) CU_TRY(cudaEventRecord(pe[0], s));
-        launch_prepass(a, r, s);
+        launch_prepass(a, r, (uint32_t)p, s);
         if (pe) CU_TRY(cudaEventRecord(pe[1], s));
         launch_huffman(a, r, s);
         launch_huffman_sync(a, r, s);
