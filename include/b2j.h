@@ -240,7 +240,8 @@ typedef struct b2j_host_opts
     int32_t n_threads;   /* host threads that parse headers and stage scans into pinned memory; 0 = as many as
                           * the machine offers, at most 8                                                        */
     int32_t group;       /* images per pipeline group (0 = 32): a group is uploaded, decoded and read back as one */
-    int32_t reserved[4]; /* 0                                                                                     */
+    int32_t group_mb;    /* and at most this many MiB of files per group (0 = 12): one host thread stages a group  */
+    int32_t reserved[3]; /* 0                                                                                     */
 } b2j_host_opts;
 
 /* b2j_decode_host() with options: the pixels arrive in opts->out_format (RGB24 moves 25 % fewer bytes over PCIe,

@@ -64,7 +64,7 @@ class BatchInfo(ctypes.Structure):
 class HostOpts(ctypes.Structure):
     """b2j_host_opts"""
     _fields_ = [("gate", ctypes.c_int32), ("out_format", ctypes.c_int32), ("n_threads", ctypes.c_int32), ("group", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 4)]
+                ("group_mb", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
 
 
 class StageTimes(ctypes.Structure):
@@ -177,13 +177,13 @@ class HostArgs:
     """The argument arrays of a b2j_decode_host* call, marshalled once (8192 small files cost tens of milliseconds of
     ctypes work per call otherwise): files / lens / outs as for Decoder.decode_host_ex."""
 
-    def __init__(self, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0):
+    def __init__(self, files, lens=None, outs=None, gate=GATE_EXTENDED, out_format=OUT_BGRA, n_threads=0, group=0, group_mb=0):
         self.n = len(files)
         self.files = files                      # keeps the bytes objects alive
         lens = lens if lens is not None else [len(f) for f in files]
         self.outs, self.fp, self.op = _host_call_args(files, outs, gate, out_format)
         self.ln = (ctypes.c_size_t * self.n)(*lens)
-        self.opts = HostOpts(gate=gate, out_format=out_format, n_threads=n_threads, group=group)
+        self.opts = HostOpts(gate=gate, out_format=out_format, n_threads=n_threads, group=group, group_mb=group_mb)
         self.status = np.zeros(self.n, np.int32)
 
 
